@@ -1,0 +1,191 @@
+/*
+ * radfoam_b200.h -- C ABI of the B200-native drop-in for radfoam's src/tracing
+ * hot path (the differentiable Voronoi ray tracer).
+ *
+ * Every entry point replaces one piece of the reference's native interface
+ * (paths relative to the radfoam tree):
+ *
+ *   rfb_create_pipeline      <- radfoam::create_pipeline            src/tracing/pipeline.h:133 (impl pipeline.cu:776-805)
+ *   rfb_attribute_dim/type   <- Pipeline::attribute_dim/_type       src/tracing/pipeline.h:128-130
+ *   rfb_prefetch_adjacent_diff <- radfoam::prefetch_adjacent_diff   src/tracing/pipeline.h:50-56
+ *   rfb_trace_forward        <- Pipeline::trace_forward             src/tracing/pipeline.h:62-78
+ *   rfb_trace_backward       <- Pipeline::trace_backward            src/tracing/pipeline.h:80-100
+ *   rfb_trace_benchmark      <- Pipeline::trace_benchmark           src/tracing/pipeline.h:117-126
+ *
+ * The reference interface is a C++ vtable taking raw device pointers (Eigen
+ * types appear only as reinterpret_casts of packed floats); this header
+ * flattens the same argument lists to POD so any FFI (ctypes, pybind11, cgo...)
+ * can bind it.  All array arguments are DEVICE pointers on the current CUDA
+ * device; `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream, which is what the reference launches on, common_kernels.cuh:34-39).
+ *
+ * Conventions:
+ *   - every function returns 0 on success, nonzero on failure; the message of
+ *     the last failure on the calling thread is rfb_last_error()  (the
+ *     reference throws std::runtime_error, cuda_helpers.h:12-30).
+ *   - layouts are the reference's: points[N][3] f32; attributes[N][A] row-major
+ *     (A = 1 + 3*(deg+1)^2: SH coefficients interleaved RGB then density,
+ *     sh_utils.cuh:78-80, pipeline.cu:49) in f32 or f16; point_adjacency[E] u32
+ *     and point_adjacency_offsets[N+1] u32 (CSR, rows ascending,
+ *     delaunay.cu:146-226); rays[R][6] f32 = origin, direction (camera.h:7-10);
+ *     start_point_index[R] u32; depth_quantiles[R][Q] f32.
+ *   - outputs are the reference's: ray_rgba[R][4] (attr dtype),
+ *     quantile_depths[R][Q] f32, quantile_point_indices[R][Q] u32,
+ *     num_intersections[R] u32, point_contribution[N] (attr dtype, caller
+ *     zero-initialises), points_grad[N][3] f32, attribute_grad[N][A] (attr
+ *     dtype), point_error[N] (attr dtype, caller zero-initialises).
+ *     Unlike the reference, points_grad / attribute_grad are fully
+ *     OVERWRITTEN by rfb_trace_backward (no caller zero-fill needed; a
+ *     zero-filled buffer gives the same result).  ray_grad is accepted and
+ *     never written, exactly like the reference kernel (pipeline.cu:132-343).
+ *   - the pipeline object owns only its own scratch (cached, re-laid-out
+ *     mirrors of the scene and the fp32 gradient accumulator); it never frees
+ *     or retains caller memory beyond a call.
+ */
+#ifndef RADFOAM_B200_H
+#define RADFOAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFB_ABI_VERSION 1
+
+/* radfoam::ScalarType subset accepted by create_pipeline (src/utils/typing.h:22-29) */
+enum { RFB_FLOAT32 = 0, RFB_FLOAT16 = 1 };
+
+/* radfoam::CameraModel, src/tracing/camera.h:12-15 */
+enum { RFB_PINHOLE = 0, RFB_FISHEYE = 1 };
+
+/* radfoam::TraceSettings, src/tracing/pipeline.h:10-20 */
+typedef struct rfb_trace_settings {
+    float weight_threshold;     /* default 0.001f */
+    uint32_t max_intersections; /* default 1024   */
+} rfb_trace_settings;
+
+/* radfoam::Camera, src/tracing/camera.h:17-34 (CVec3f = 3 packed floats) */
+typedef struct rfb_camera {
+    float position[3];
+    float forward[3];
+    float right[3];
+    float up[3];
+    float fov;
+    uint32_t width;
+    uint32_t height;
+    int32_t model; /* RFB_PINHOLE / RFB_FISHEYE */
+} rfb_camera;
+
+/* Optional per-call hints; NULL means all-zero (always safe, never changes results). */
+typedef struct rfb_launch_opts {
+    /* Nonzero: identifies the contents of (points, attributes, adjacency).  When
+     * two consecutive calls on one pipeline pass the same nonzero value and the
+     * same device pointers / sizes, the re-laid-out scene mirrors (the
+     * reference's adjacent_diff among them, which it rebuilds on every call,
+     * pipeline.cu:613-620, 667-674) are reused instead of rebuilt.  0 = rebuild. */
+    uint64_t scene_version;
+    /* Nonzero: rays form a row-major image of this width (R % width == 0); rays
+     * are then assigned to warps as 8x4 pixel tiles for cell coherence.
+     * 0 = rays are an unordered batch (linear assignment).  Results are
+     * identical either way (up to fp32 summation order of the scatter-adds). */
+    uint32_t image_width;
+    uint32_t flags; /* RFB_FLAG_* */
+} rfb_launch_opts;
+
+/* zero non-finite gradient entries in the backward epilogue (what
+ * radfoam_model/render.py:98-99 does in two extra passes after the call) */
+#define RFB_FLAG_SCRUB_NONFINITE 1u
+
+typedef struct rfb_pipeline rfb_pipeline;
+
+const char *rfb_last_error(void);
+int rfb_abi_version(void);
+
+/* sh_degree in {0,1,2,3}, attr_dtype in {RFB_FLOAT32, RFB_FLOAT16}; anything else
+ * fails ("Unsupported SH degree" / "Unsupported attribute type", pipeline.cu:776-805). */
+int rfb_create_pipeline(int sh_degree, int attr_dtype, rfb_pipeline **out);
+void rfb_destroy_pipeline(rfb_pipeline *pipeline);
+uint32_t rfb_attribute_dim(const rfb_pipeline *pipeline);
+int rfb_attribute_type(const rfb_pipeline *pipeline);
+
+/* adjacent_diff[e] = half4(RN(points[adj[e]] - points[i]), 0) for e in row i;
+ * adjacent_diff has room for point_adjacency_size half4 (8-byte) entries. */
+int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points,
+                               uint32_t point_adjacency_size,
+                               const uint32_t *point_adjacency,
+                               const uint32_t *point_adjacency_offsets,
+                               void *adjacent_diff, void *stream);
+
+int rfb_trace_forward(rfb_pipeline *pipeline, const rfb_trace_settings *settings,
+                      uint32_t num_points, const float *points,
+                      const void *attributes, uint32_t point_adjacency_size,
+                      const uint32_t *point_adjacency,
+                      const uint32_t *point_adjacency_offsets, uint32_t num_rays,
+                      const float *rays, const uint32_t *start_point_index,
+                      uint32_t num_depth_quantiles, const float *depth_quantiles,
+                      void *ray_rgba, float *quantile_depths,
+                      uint32_t *quantile_point_indices,
+                      uint32_t *num_intersections, void *point_contribution,
+                      const rfb_launch_opts *opts, void *stream);
+
+int rfb_trace_backward(rfb_pipeline *pipeline, const rfb_trace_settings *settings,
+                       uint32_t num_points, const float *points,
+                       const void *attributes, uint32_t point_adjacency_size,
+                       const uint32_t *point_adjacency,
+                       const uint32_t *point_adjacency_offsets, uint32_t num_rays,
+                       const float *rays, const uint32_t *start_point_index,
+                       uint32_t num_depth_quantiles, const float *depth_quantiles,
+                       const uint32_t *quantile_point_indices,
+                       const void *ray_rgba, const void *ray_rgba_grad,
+                       const float *depth_grad, const void *ray_error,
+                       float *ray_grad, float *points_grad, void *attribute_grad,
+                       void *point_error, const rfb_launch_opts *opts,
+                       void *stream);
+
+/* ---- split backward for ray-sharded multi-GPU use ----
+ * rfb_trace_backward == accumulate (zeroes then fills the pipeline's fp32
+ * accumulator [N][rfb_grad_row_floats]) + finalize (writes the reference-layout
+ * outputs).  A data-parallel caller all-reduces the accumulator between them. */
+int rfb_trace_backward_accumulate(
+    rfb_pipeline *pipeline, const rfb_trace_settings *settings,
+    uint32_t num_points, const float *points, const void *attributes,
+    uint32_t point_adjacency_size, const uint32_t *point_adjacency,
+    const uint32_t *point_adjacency_offsets, uint32_t num_rays,
+    const float *rays, const uint32_t *start_point_index,
+    uint32_t num_depth_quantiles, const float *depth_quantiles,
+    const uint32_t *quantile_point_indices, const void *ray_rgba,
+    const void *ray_rgba_grad, const float *depth_grad, const void *ray_error,
+    void *point_error, const rfb_launch_opts *opts, void *stream);
+/* device pointer + element count of the fp32 accumulator of the last accumulate */
+int rfb_grad_accumulator(rfb_pipeline *pipeline, float **ptr, uint64_t *num_floats);
+uint32_t rfb_grad_row_floats(const rfb_pipeline *pipeline);
+int rfb_trace_backward_finalize(rfb_pipeline *pipeline, uint32_t num_points,
+                                float *points_grad, void *attribute_grad,
+                                uint32_t flags, void *stream);
+
+/* forward-only render with in-kernel ray generation (camera.h:56-85) and RGBA8
+ * packing (tracing_utils.cuh:105-115).  adjacent_diff is the caller-built
+ * half4[E] array exactly as the reference takes it (benchmark.py:41-54);
+ * start_point_index points at ONE u32; output_rgba is u32[width*height]. */
+int rfb_trace_benchmark(rfb_pipeline *pipeline, const rfb_trace_settings *settings,
+                        uint32_t num_points, const float *points,
+                        const void *attributes,
+                        const uint32_t *point_adjacency,
+                        const uint32_t *point_adjacency_offsets,
+                        const void *adjacent_diff, const rfb_camera *camera,
+                        const uint32_t *start_point_index, uint32_t *output_rgba,
+                        const rfb_launch_opts *opts, void *stream);
+
+/* kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches) */
+uint64_t rfb_launch_count(void);
+void rfb_reset_launch_count(void);
+
+/* drop cached scene mirrors (next call rebuilds) */
+void rfb_invalidate_cache(rfb_pipeline *pipeline);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADFOAM_B200_H */

@@ -1,0 +1,286 @@
+// Device-side building blocks of the B200 foam tracer (sm_100a).
+//
+// Behavioural spec: SURVEY.md Appendix A, i.e. radfoam's
+//   src/tracing/tracing_utils.cuh:8-103  (cell walk, intersection gradient)
+//   src/tracing/sh_utils.cuh:8-92        (SH basis, SH -> rgb, rgb-grad -> SH)
+//   src/tracing/pipeline.cu:14-343       (forward / backward cell functors)
+// Nothing here is shared with the reference's code; the arithmetic that decides
+// the integer traversal is pinned with non-contractable intrinsics in the
+// association the reference's own sm_100 SASS uses (see walk_face()).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rfb {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kBlock = 128; // threads per CTA in the ray kernels
+
+__host__ __device__ constexpr int sh_dim(int deg) { return (deg + 1) * (deg + 1); }
+// floats per row of the internal SH mirror (3*sh_dim padded to a multiple of 4)
+__host__ __device__ constexpr int sh_row(int deg) { return (3 * sh_dim(deg) + 3) & ~3; }
+// floats per row of the gradient accumulator: [SH row][density, gx, gy, gz]
+__host__ __device__ constexpr int grad_row(int deg) { return sh_row(deg) + 4; }
+__host__ __device__ constexpr int attr_dim(int deg) { return 1 + 3 * sh_dim(deg); }
+
+// first slot of row `i` in the padded face arrays: even (16-byte aligned rows),
+// rows never overlap, at most one slack slot per row, no prefix scan needed.
+__host__ __device__ __forceinline__ uint32_t padded_begin(uint32_t off_i, uint32_t i) {
+    return (off_i + i + 1u) & ~1u;
+}
+
+// ---------------------------------------------------------------- loads
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ uint4 ldg4(const uint4 *p) { return __ldg(p); }
+__device__ __forceinline__ uint2 ldg2(const uint2 *p) { return __ldg(p); }
+
+// 16-byte fire-and-forget reduction (sm_90+): one L2 atomic transaction for four
+// consecutive floats instead of four scalar REDs.
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
+                 "f"(c), "f"(d)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- SH basis
+// Real SH basis of the (unit) direction; same formulas and evaluation order as
+// sh_coefficients<deg>() (sh_utils.cuh:34-70) so nvcc contracts them alike.
+template <int DEG>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float *sh) {
+    constexpr float C0 = 0.28209479177387814f;
+    constexpr float C1 = 0.4886025119029199f;
+    sh[0] = C0;
+    if (DEG > 0) {
+        sh[1] = -C1 * y;
+        sh[2] = C1 * z;
+        sh[3] = -C1 * x;
+    }
+    float xx = x * x, yy = y * y, zz = z * z;
+    float xy = x * y, yz = y * z, xz = x * z;
+    if (DEG > 1) {
+        sh[4] = 1.0925484305920792f * xy;
+        sh[5] = -1.0925484305920792f * yz;
+        sh[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+        sh[7] = -1.0925484305920792f * xz;
+        sh[8] = 0.5462742152960396f * (xx - yy);
+    }
+    if (DEG > 2) {
+        sh[9] = -0.5900435899266435f * y * (3.0f * xx - yy);
+        sh[10] = 2.890611442640554f * xy * z;
+        sh[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
+        sh[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+        sh[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
+        sh[14] = 1.445305721320277f * z * (xx - yy);
+        sh[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
+    }
+}
+
+// rgb = max(0, 0.5 + sum_k Y_k * c_k) per channel, accumulated k ascending in one
+// FFMA chain per channel (load_sh_as_rgb, sh_utils.cuh:72-83).  `row` is the
+// 16-byte aligned internal SH row [3*sh_dim floats, channel-interleaved][pad].
+template <int DEG>
+__device__ __forceinline__ void sh_to_rgb(const float *__restrict__ row, const float *sh,
+                                          float &r, float &g, float &b) {
+    constexpr int NV = sh_row(DEG) / 4;
+    float v[NV * 4];
+    const float4 *row4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float4 q = ldg4(row4 + i);
+        v[4 * i + 0] = q.x;
+        v[4 * i + 1] = q.y;
+        v[4 * i + 2] = q.z;
+        v[4 * i + 3] = q.w;
+    }
+    float rgb[3] = {0.5f, 0.5f, 0.5f};
+#pragma unroll
+    for (int i = 0; i < 3 * sh_dim(DEG); ++i)
+        rgb[i % 3] = __fmaf_rn(sh[i / 3], v[i], rgb[i % 3]);
+    // cwiseMax(0): (x < 0) ? 0 : x  (NaN stays NaN, as in the reference build)
+    r = (rgb[0] < 0.0f) ? 0.0f : rgb[0];
+    g = (rgb[1] < 0.0f) ? 0.0f : rgb[1];
+    b = (rgb[2] < 0.0f) ? 0.0f : rgb[2];
+}
+
+// ---------------------------------------------------------------- the walk
+struct RayGeom {
+    float ox, oy, oz; // origin
+    float dx, dy, dz; // unit direction
+};
+
+// ray.direction /= ray.direction.norm()  (pipeline.cu:39-40): squared norm in the
+// x0 + (x1 + x2) order with the two fusions nvcc applies, IEEE sqrt and division.
+__device__ __forceinline__ void normalize_dir(float &x, float &y, float &z) {
+    float n2 = __fmaf_rn(x, x, __fmaf_rn(y, y, __fmul_rn(z, z)));
+    float n = __fsqrt_rn(n2);
+    x = __fdiv_rn(x, n);
+    y = __fdiv_rn(y, n);
+    z = __fdiv_rn(z, n);
+}
+
+// One bisector-plane test (tracing_utils.cuh:52-65).  `h` is one face record:
+// (dx, dy, dz, 0) in fp16 = RN_half(neighbour - cell point).  Association as in
+// the reference's SASS (re-read from oracle/_ref):
+//   f   = fma(o, 0.5, P)            per component
+//   dp  = fma(ox, dx, fma(oy, dy, oz*dz))
+//   num = fma(ox, fx-rx, fma(oy, fy-ry, oz*(fz-rz)))
+//   t   = num / dp   (IEEE)
+__device__ __forceinline__ void walk_face(uint2 h, float px, float py, float pz,
+                                          const RayGeom &ray, float &t, float &dp) {
+    __half2 hxy = *reinterpret_cast<__half2 *>(&h.x);
+    __half2 hzw = *reinterpret_cast<__half2 *>(&h.y);
+    float ox = __low2float(hxy), oy = __high2float(hxy), oz = __low2float(hzw);
+    float fx = __fmaf_rn(ox, 0.5f, px);
+    float fy = __fmaf_rn(oy, 0.5f, py);
+    float fz = __fmaf_rn(oz, 0.5f, pz);
+    dp = __fmaf_rn(ox, ray.dx, __fmaf_rn(oy, ray.dy, __fmul_rn(oz, ray.dz)));
+    float num = __fmaf_rn(ox, __fsub_rn(fx, ray.ox),
+                          __fmaf_rn(oy, __fsub_rn(fy, ray.oy), __fmul_rn(oz, __fsub_rn(fz, ray.oz))));
+    t = __fdiv_rn(num, dp);
+}
+
+// Scene views the walk reads.  Two face layouts:
+//  * PaddedFaces: this library's own mirror. Rows start at padded_begin() (even
+//    slot => 16-byte aligned), so two faces arrive per 128-bit load; the
+//    neighbour index of a face sits at the same slot of `nbr`.  Unused slots
+//    hold zero faces (dp == 0 never wins).
+//  * CallerFaces: the caller's CSR + a caller-built half4[E] array (what
+//    trace_benchmark takes, pipeline.h:117-126); 64-bit loads.
+struct PaddedFaces {
+    const uint2 *faces;
+    const uint32_t *nbr;
+    const uint32_t *off;
+    __device__ __forceinline__ void row(uint32_t cell, uint32_t &begin, uint32_t &nf) const {
+        uint32_t a = __ldg(off + cell), b = __ldg(off + cell + 1);
+        begin = padded_begin(a, cell);
+        nf = b - a;
+    }
+    // first-minimum scan over the row: strict `<`, faces in array order
+    __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
+                                         const RayGeom &ray, float &t1, uint32_t &face) const {
+        const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
+        for (uint32_t f = 0; f < nf; f += 4) {
+            uint4 a = ldg4(p + (f >> 1));
+            uint4 b = ldg4(p + (f >> 1) + 1); // may over-read into the next row / tail pad
+            float t, dp;
+            walk_face(make_uint2(a.x, a.y), px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
+            walk_face(make_uint2(a.z, a.w), px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1 && f + 1 < nf) { t1 = t; face = f + 1; }
+            walk_face(make_uint2(b.x, b.y), px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1 && f + 2 < nf) { t1 = t; face = f + 2; }
+            walk_face(make_uint2(b.z, b.w), px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1 && f + 3 < nf) { t1 = t; face = f + 3; }
+        }
+    }
+    __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {
+        return __ldg(nbr + begin + face);
+    }
+};
+
+struct CallerFaces {
+    const uint2 *faces; // half4[E], caller CSR order
+    const uint32_t *adj;
+    const uint32_t *off;
+    __device__ __forceinline__ void row(uint32_t cell, uint32_t &begin, uint32_t &nf) const {
+        uint32_t a = __ldg(off + cell), b = __ldg(off + cell + 1);
+        begin = a;
+        nf = b - a;
+    }
+    __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
+                                         const RayGeom &ray, float &t1, uint32_t &face) const {
+        const uint2 *p = faces + begin;
+        uint32_t f = 0;
+        for (; f + 2 <= nf; f += 2) {
+            uint2 a = ldg2(p + f);
+            uint2 b = ldg2(p + f + 1);
+            float t, dp;
+            walk_face(a, px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
+            walk_face(b, px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1) { t1 = t; face = f + 1; }
+        }
+        if (f < nf) {
+            uint2 a = ldg2(p + f);
+            float t, dp;
+            walk_face(a, px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
+        }
+    }
+    __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {
+        return __ldg(adj + begin + face);
+    }
+};
+
+// The per-ray cell walk (trace<>, tracing_utils.cuh:8-89).  cells[i] =
+// (point.xyz, density).  `cell_fn(cell, density, t0, t1, P, Pnext)` is called
+// for every cell with t1 > t0 and returns false to stop.  Returns n = cells
+// entered (max_steps + 1 when the budget ran out).
+template <typename Faces, typename CellFn>
+__device__ __forceinline__ uint32_t walk(const Faces &fa, const float4 *__restrict__ cells,
+                                         const RayGeom &ray, uint32_t start, uint32_t max_steps,
+                                         CellFn &&cell_fn) {
+    float t0 = 0.0f;
+    uint32_t n = 0;
+    uint32_t cur = start;
+    float4 pc = ldg4(cells + cur);
+    for (;;) {
+        n++;
+        if (n > max_steps)
+            break;
+        uint32_t begin, nf;
+        fa.row(cur, begin, nf);
+        float t1 = __int_as_float(0x7f800000);
+        uint32_t face = kNone;
+        fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+        if (face == kNone)
+            break;
+        uint32_t nxt = fa.neighbour(begin, face);
+        float4 pn = ldg4(cells + nxt);
+        if (t1 > t0) {
+            if (!cell_fn(cur, pc, t0, t1, pn))
+                break;
+        }
+        t0 = fmaxf(t0, t1);
+        cur = nxt;
+        pc = pn;
+    }
+    return n;
+}
+
+// d t / d p of the ray / bisector(p, q) intersection (cell_intersection_grad,
+// tracing_utils.cuh:91-103), from the fp32 points.
+__device__ __forceinline__ void isect_grad(float px, float py, float pz, float qx, float qy,
+                                           float qz, const RayGeom &ray, float &gx, float &gy,
+                                           float &gz) {
+    float fox = (px + qx) / 2.0f, foy = (py + qy) / 2.0f, foz = (pz + qz) / 2.0f;
+    float nx = qx - px, ny = qy - py, nz = qz - pz;
+    float num = (fox - ray.ox) * nx + ((foy - ray.oy) * ny + (foz - ray.oz) * nz);
+    float dp = nx * ray.dx + (ny * ray.dy + nz * ray.dz);
+    float inv = dp * dp;
+    gx = (num * ray.dx + dp * (ray.ox - px)) / inv;
+    gy = (num * ray.dy + dp * (ray.oy - py)) / inv;
+    gz = (num * ray.dz + dp * (ray.oz - pz)) / inv;
+}
+
+// ray index of this thread.  image_width == 0: linear.  Otherwise the rays are a
+// row-major image; a CTA of 128 threads covers a 16x8 pixel block and each warp
+// an 8x4 tile, so the lanes of a warp sit in the same or adjacent cells.
+__device__ __forceinline__ bool thread_ray(uint32_t num_rays, uint32_t image_width,
+                                           uint32_t blocks_x, uint32_t &ray_idx) {
+    if (image_width == 0) {
+        ray_idx = blockIdx.x * kBlock + threadIdx.x;
+        return ray_idx < num_rays;
+    }
+    uint32_t bx = blockIdx.x % blocks_x, by = blockIdx.x / blocks_x;
+    uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t x = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    uint32_t y = by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    uint32_t height = num_rays / image_width;
+    ray_idx = y * image_width + x;
+    return x < image_width && y < height;
+}
+
+} // namespace rfb

@@ -1,0 +1,492 @@
+// Kernels of the B200 foam tracer: scene re-layout, forward, backward, benchmark.
+// See foam_device.cuh for the spec references.
+#pragma once
+
+#include "foam_device.cuh"
+
+namespace rfb {
+
+// ------------------------------------------------------------------ re-layout
+// cells[i] = (point, density); sh_rows[i] = SH coefficients padded to 16 bytes.
+// Replaces per-step gathers of 3 + 49 scalars by aligned 128-bit loads.
+template <typename AttrT>
+__global__ void build_cells_kernel(const float *__restrict__ points,
+                                   const AttrT *__restrict__ attrs, uint32_t num_points,
+                                   int attr_dim_, int sh_row_, float4 *__restrict__ cells,
+                                   float *__restrict__ sh_rows) {
+    // one thread per (point, slot) element of the SH mirror; slot 0 also writes the cell
+    uint64_t total = (uint64_t)num_points * (uint32_t)sh_row_;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t i = (uint32_t)(idx / (uint32_t)sh_row_);
+        int s = (int)(idx - (uint64_t)i * (uint32_t)sh_row_);
+        const AttrT *row = attrs + (uint64_t)i * attr_dim_;
+        float v = (s < attr_dim_ - 1) ? (float)row[s] : 0.0f;
+        sh_rows[idx] = v;
+        if (s == 0) {
+            float dens = (float)row[attr_dim_ - 1];
+            cells[i] = make_float4(points[3 * (uint64_t)i], points[3 * (uint64_t)i + 1],
+                                   points[3 * (uint64_t)i + 2], dens);
+        }
+    }
+}
+
+// faces[padded_begin(i) + f] = half4(RN(points[adj[e]] - points[i]), 0),
+// nbr[...] = adj[e]  (the reference's prefetch_adjacent_diff_kernel,
+// pipeline.cu:546-568, writes the same values in CSR order).  16 lanes per row.
+__global__ void build_faces_kernel(const float *__restrict__ points, uint32_t num_points,
+                                   const uint32_t *__restrict__ adj,
+                                   const uint32_t *__restrict__ off, uint2 *__restrict__ faces,
+                                   uint32_t *__restrict__ nbr) {
+    uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    uint32_t lane = threadIdx.x & 15;
+    uint32_t stride = (gridDim.x * blockDim.x) >> 4;
+    for (uint32_t i = group; i < num_points; i += stride) {
+        uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
+        uint32_t dst = padded_begin(a, i);
+        float px = __ldg(points + 3 * (uint64_t)i), py = __ldg(points + 3 * (uint64_t)i + 1),
+              pz = __ldg(points + 3 * (uint64_t)i + 2);
+        for (uint32_t f = lane; f < b - a; f += 16) {
+            uint32_t j = __ldg(adj + a + f);
+            float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
+                  qz = __ldg(points + 3 * (uint64_t)j + 2);
+            __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
+            __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
+            uint2 rec;
+            rec.x = *reinterpret_cast<uint32_t *>(&hxy);
+            rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+            faces[dst + f] = rec;
+            nbr[dst + f] = j;
+        }
+    }
+}
+
+// reference-layout adjacent_diff (CSR order), for rfb_prefetch_adjacent_diff
+__global__ void adjacent_diff_kernel(const float *__restrict__ points, uint32_t num_points,
+                                     const uint32_t *__restrict__ adj,
+                                     const uint32_t *__restrict__ off, uint2 *__restrict__ out) {
+    uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    uint32_t lane = threadIdx.x & 15;
+    uint32_t stride = (gridDim.x * blockDim.x) >> 4;
+    for (uint32_t i = group; i < num_points; i += stride) {
+        uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
+        float px = __ldg(points + 3 * (uint64_t)i), py = __ldg(points + 3 * (uint64_t)i + 1),
+              pz = __ldg(points + 3 * (uint64_t)i + 2);
+        for (uint32_t e = a + lane; e < b; e += 16) {
+            uint32_t j = __ldg(adj + e);
+            float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
+                  qz = __ldg(points + 3 * (uint64_t)j + 2);
+            __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
+            __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
+            uint2 rec;
+            rec.x = *reinterpret_cast<uint32_t *>(&hxy);
+            rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+            out[e] = rec;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward
+struct ForwardParams {
+    const float4 *cells;
+    const float *sh_rows;
+    const float *rays;
+    const uint32_t *start;
+    const float *quantiles; // [R][Q] or null
+    void *rgba;             // [R][4] f32 or f16
+    float *qdepth;          // [R][Q]
+    uint32_t *qidx;         // [R][Q]
+    uint32_t *nint;         // [R] or null
+    void *contrib;          // [N] f32 or f16, or null
+    uint32_t num_rays;
+    uint32_t num_q;
+    uint32_t image_width;
+    uint32_t blocks_x;
+    float weight_threshold;
+    uint32_t max_steps;
+    int out_half;
+};
+
+template <int DEG, typename Faces>
+__global__ void __launch_bounds__(kBlock) forward_kernel(const ForwardParams p, const Faces fa) {
+    uint32_t r;
+    if (!thread_ray(p.num_rays, p.image_width, p.blocks_x, r))
+        return;
+
+    RayGeom ray;
+    {
+        const float *rp = p.rays + 6 * (uint64_t)r;
+        ray.ox = __ldg(rp + 0);
+        ray.oy = __ldg(rp + 1);
+        ray.oz = __ldg(rp + 2);
+        ray.dx = __ldg(rp + 3);
+        ray.dy = __ldg(rp + 4);
+        ray.dz = __ldg(rp + 5);
+        normalize_dir(ray.dx, ray.dy, ray.dz);
+    }
+    float sh[sh_dim(DEG)];
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+
+    const uint32_t Q = p.quantiles ? p.num_q : 0u;
+    const float *qv = p.quantiles + (uint64_t)r * p.num_q;
+    uint32_t qi = 0;
+    float cq = Q ? __ldg(qv) : 0.0f;
+
+    float T = 1.0f;
+    float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+
+    auto cell_fn = [&](uint32_t cell, const float4 &pc, float t0, float t1, const float4 &) -> bool {
+        float s = pc.w;
+        float r_ = 0.0f, g_ = 0.0f, b_ = 0.0f;
+        if (s > 1e-6f)
+            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cell * sh_row(DEG), sh, r_, g_, b_);
+        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+        float alpha = 1.0f - expf(-s * delta);
+        float w = __fmul_rn(T, alpha);
+        if (p.contrib) {
+            if (p.out_half)
+                atomicAdd(reinterpret_cast<__half *>(p.contrib) + cell, __float2half_rn(w));
+            else
+                atomicAdd(reinterpret_cast<float *>(p.contrib) + cell, w);
+        }
+        cr = __fmaf_rn(w, r_, cr);
+        cg = __fmaf_rn(w, g_, cg);
+        cb = __fmaf_rn(w, b_, cb);
+        float Tn = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        while (qi < Q && Tn < cq) {
+            p.qdepth[(uint64_t)r * Q + qi] = __fadd_rn(t0, __fdiv_rn(logf(__fdiv_rn(T, cq)), s));
+            p.qidx[(uint64_t)r * Q + qi] = cell;
+            qi++;
+            if (qi < Q)
+                cq = __ldg(qv + qi);
+        }
+        T = Tn;
+        return T > p.weight_threshold;
+    };
+
+    uint32_t n = walk(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn);
+
+    while (qi < Q) {
+        p.qdepth[(uint64_t)r * Q + qi] = -1.0f;
+        p.qidx[(uint64_t)r * Q + qi] = kNone;
+        qi++;
+    }
+    float a = __fsub_rn(1.0f, T);
+    if (p.out_half) {
+        __half2 lo = __floats2half2_rn(cr, cg), hi = __floats2half2_rn(cb, a);
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t *>(&lo);
+        v.y = *reinterpret_cast<uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(p.rgba)[r] = v;
+    } else {
+        reinterpret_cast<float4 *>(p.rgba)[r] = make_float4(cr, cg, cb, a);
+    }
+    if (p.nint)
+        p.nint[r] = n;
+}
+
+// ------------------------------------------------------------------ backward
+struct BackwardParams {
+    const float4 *cells;
+    const float *sh_rows;
+    const float *rays;
+    const uint32_t *start;
+    const float *quantiles;
+    const uint32_t *qidx;
+    const void *rgba;      // saved forward output [R][4]
+    const void *rgba_grad; // [R][4]
+    const float *depth_grad;
+    const void *ray_error; // [R] or null
+    void *point_error;     // [N] or null
+    float *acc;            // [N][grad_row] fp32 accumulator
+    uint32_t num_rays;
+    uint32_t num_q;
+    uint32_t image_width;
+    uint32_t blocks_x;
+    float weight_threshold;
+    uint32_t max_steps;
+    int io_half;
+};
+
+template <int DEG, typename Faces>
+__global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p, const Faces fa) {
+    uint32_t r;
+    if (!thread_ray(p.num_rays, p.image_width, p.blocks_x, r))
+        return;
+    constexpr int GR = grad_row(DEG);
+    constexpr int SR = sh_row(DEG);
+
+    RayGeom ray;
+    {
+        const float *rp = p.rays + 6 * (uint64_t)r;
+        ray.ox = __ldg(rp + 0);
+        ray.oy = __ldg(rp + 1);
+        ray.oz = __ldg(rp + 2);
+        ray.dx = __ldg(rp + 3);
+        ray.dy = __ldg(rp + 4);
+        ray.dz = __ldg(rp + 5);
+        normalize_dir(ray.dx, ray.dy, ray.dz);
+    }
+    float sh[sh_dim(DEG)];
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+
+    float out[4], g[4], err = 0.0f;
+    if (p.io_half) {
+        const __half *o = reinterpret_cast<const __half *>(p.rgba) + 4 * (uint64_t)r;
+        const __half *gg = reinterpret_cast<const __half *>(p.rgba_grad) + 4 * (uint64_t)r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            out[c] = __half2float(o[c]);
+            g[c] = __half2float(gg[c]);
+        }
+        if (p.ray_error)
+            err = __half2float(reinterpret_cast<const __half *>(p.ray_error)[r]);
+    } else {
+        float4 o = __ldg(reinterpret_cast<const float4 *>(p.rgba) + r);
+        float4 gg = __ldg(reinterpret_cast<const float4 *>(p.rgba_grad) + r);
+        out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
+        g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+        if (p.ray_error)
+            err = __ldg(reinterpret_cast<const float *>(p.ray_error) + r);
+    }
+
+    const uint32_t Q = p.quantiles ? p.num_q : 0u;
+    const float *qv = p.quantiles + (uint64_t)r * p.num_q;
+    const float *dg = p.depth_grad + (uint64_t)r * p.num_q;
+    uint32_t qi = 0;
+    float cq = Q ? __ldg(qv) : 0.0f;
+    float cdg = 0.0f; // pipeline.cu:196-207
+    for (uint32_t i = 0; i < Q; ++i) {
+        uint32_t pi = __ldg(p.qidx + (uint64_t)r * Q + i);
+        if (pi != kNone)
+            cdg += __ldg(dg + i) / ldg4(p.cells + pi).w;
+    }
+
+    float T = 1.0f;
+    float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    uint32_t prev = kNone;
+    float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;    // prev_point
+    float pgx = 0.0f, pgy = 0.0f, pgz = 0.0f;    // prev_point_grad
+    float cgx = 0.0f, cgy = 0.0f, cgz = 0.0f;    // current_point_grad
+
+    auto cell_fn = [&](uint32_t cell, const float4 &pc, float t0, float t1, const float4 &pn) -> bool {
+        float s = pc.w;
+        float rgb[3] = {0.0f, 0.0f, 0.0f};
+        if (s > 1e-6f)
+            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cell * SR, sh, rgb[0], rgb[1], rgb[2]);
+        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+        float alpha = 1.0f - expf(-s * delta);
+        float w = __fmul_rn(T, alpha);
+        float one_m_alpha = __fsub_rn(1.0f, alpha);
+        float dalpha_ds = delta * one_m_alpha;
+        float dalpha_dd = (delta > 0.0f) ? s * one_m_alpha : 0.0f;
+        cr = __fmaf_rn(w, rgb[0], cr);
+        cg = __fmaf_rn(w, rgb[1], cg);
+        cb = __fmaf_rn(w, rgb[2], cb);
+        if (p.point_error) {
+            if (p.io_half)
+                atomicAdd(reinterpret_cast<__half *>(p.point_error) + cell, __float2half_rn(w * err));
+            else
+                atomicAdd(reinterpret_cast<float *>(p.point_error) + cell, w * err);
+        }
+        float dL_drgb[3] = {g[0] * w, g[1] * w, g[2] * w};
+        float denom = T * (one_m_alpha + 1e-6f);
+        float rest0 = (out[0] - cr) / denom, rest1 = (out[1] - cg) / denom, rest2 = (out[2] - cb) / denom;
+        float dL_dalpha = T * ((rgb[0] - rest0) * g[0] + ((rgb[1] - rest1) * g[1] + (rgb[2] - rest2) * g[2]));
+        dL_dalpha += (1.0f - out[3]) * g[3] / (one_m_alpha + 1e-6f);
+        float dL_ds = dL_dalpha * dalpha_ds;
+        float dL_dd = dL_dalpha * dalpha_dd;
+        float dL_dt0 = 0.0f;
+
+        float Tn = __fmul_rn(T, one_m_alpha);
+        while (qi < Q && Tn < cq) {
+            float gq = __ldg(dg + qi) / s;
+            dL_dt0 += gq;
+            dL_ds += -gq * logf(__fdiv_rn(T, cq)) / s;
+            cdg -= gq;
+            qi++;
+            if (qi < Q)
+                cq = __ldg(qv + qi);
+        }
+        if (qi < Q) {
+            dL_ds += -delta * cdg;
+            dL_dd += -s * cdg;
+        }
+        dL_dt0 += -dL_dd;
+        float dL_dt1 = dL_dd;
+
+        // position gradients through t0 / t1 (pipeline.cu:284-313, quirks A.5.1-3 kept)
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        if (prev != kNone)
+            isect_grad(ppx, ppy, ppz, pc.x, pc.y, pc.z, ray, ax, ay, az); // dt0/dprev
+        float bx, by, bz, ex, ey, ez, fx, fy, fz;
+        isect_grad(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz);   // dt1/dcur
+        isect_grad(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez);      // dt0/dcur
+        isect_grad(pn.x, pn.y, pn.z, pc.x, pc.y, pc.z, ray, fx, fy, fz);   // dt1/dnext
+        pgx += dL_dt0 * ax; pgy += dL_dt0 * ay; pgz += dL_dt0 * az;
+        cgx += dL_dt0 * ex + dL_dt1 * bx;
+        cgy += dL_dt0 * ey + dL_dt1 * by;
+        cgz += dL_dt0 * ez + dL_dt1 * bz;
+        if (prev != kNone)
+            red_add_v4(p.acc + (uint64_t)prev * GR + SR, 0.0f, pgx, pgy, pgz);
+        ppx = pc.x; ppy = pc.y; ppz = pc.z;
+        prev = cell;
+        pgx = cgx; pgy = cgy; pgz = cgz;
+        cgx = dL_dt1 * fx; cgy = dL_dt1 * fy; cgz = dL_dt1 * fz;
+
+        T = Tn;
+
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (rgb[c] == 0.0f)
+                dL_drgb[c] = 0.0f;
+        float *row = p.acc + (uint64_t)cell * GR;
+        // write_rgb_grad_to_sh (sh_utils.cuh:85-92) as 128-bit reductions; a row whose
+        // three channel gradients are all zero adds nothing and is skipped.
+        if (dL_drgb[0] != 0.0f || dL_drgb[1] != 0.0f || dL_drgb[2] != 0.0f) {
+            float v[SR];
+#pragma unroll
+            for (int i = 0; i < SR; ++i)
+                v[i] = (i < 3 * sh_dim(DEG)) ? sh[i / 3] * dL_drgb[i % 3] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < SR; i += 4)
+                red_add_v4(row + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        red_add_v4(row + SR, dL_ds, 0.0f, 0.0f, 0.0f);
+        return T > p.weight_threshold;
+    };
+
+    walk(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn);
+}
+
+// accumulator -> reference-layout gradient outputs (+ optional finite scrub)
+template <typename AttrT>
+__global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t num_points,
+                                      int attr_dim_, int sh_row_, float *__restrict__ points_grad,
+                                      AttrT *__restrict__ attr_grad, int scrub) {
+    int gr = sh_row_ + 4;
+    uint64_t total = (uint64_t)num_points * (uint32_t)attr_dim_;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t i = (uint32_t)(idx / (uint32_t)attr_dim_);
+        int s = (int)(idx - (uint64_t)i * (uint32_t)attr_dim_);
+        const float *row = acc + (uint64_t)i * gr;
+        float v = (s < attr_dim_ - 1) ? row[s] : row[sh_row_];
+        AttrT o = (AttrT)v;
+        if (scrub && !isfinite((float)o))
+            o = (AttrT)0.0f;
+        attr_grad[idx] = o;
+        if (s < 3) {
+            float gq = row[sh_row_ + 1 + s];
+            if (scrub && !isfinite(gq))
+                gq = 0.0f;
+            points_grad[3 * (uint64_t)i + s] = gq;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ benchmark
+struct CameraParams {
+    float position[3], forward[3], right[3], up[3];
+    float fov;
+    uint32_t width, height;
+    int model;
+};
+
+// cast_ray (camera.h:56-85)
+__device__ __forceinline__ void cast_ray(const CameraParams &c, int i, int j, RayGeom &ray) {
+    float aspect = (float)c.width / (float)c.height;
+    float x = (float)i / (float)c.width;
+    float y = (float)j / (float)c.height;
+    float u = (2.0f * x - 1.0f) * aspect;
+    float v = (1.0f - 2.0f * y);
+    float mask = 1.0f;
+    float d[3];
+    if (c.model == 0) {
+        float w = 1.0f / tanf(c.fov * 0.5f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            d[k] = w * c.forward[k] + u * c.right[k] + v * c.up[k];
+    } else {
+        float theta = atan2f(v, u);
+        float phi = c.fov * sqrtf(u * u + v * v);
+        if (phi >= 3.14159265358979323846f) {
+            phi = 3.14159265358979323846f - 1e-6f;
+            mask = 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            d[k] = sinf(phi) * cosf(theta) * c.right[k] + sinf(phi) * sinf(theta) * c.up[k] +
+                   cosf(phi) * c.forward[k];
+    }
+    float n2 = __fmaf_rn(d[0], d[0], __fmaf_rn(d[1], d[1], __fmul_rn(d[2], d[2])));
+    if (n2 > 0.0f) {
+        float n = __fsqrt_rn(n2);
+        d[0] = __fdiv_rn(d[0], n);
+        d[1] = __fdiv_rn(d[1], n);
+        d[2] = __fdiv_rn(d[2], n);
+    }
+    ray.ox = c.position[0];
+    ray.oy = c.position[1];
+    ray.oz = c.position[2];
+    ray.dx = d[0] * mask;
+    ray.dy = d[1] * mask;
+    ray.dz = d[2] * mask;
+}
+
+// make_rgba8 (tracing_utils.cuh:105-115): clamp, truncate
+__device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b, float a) {
+    r = fmaxf(0.0f, fminf(1.0f, r));
+    g = fmaxf(0.0f, fminf(1.0f, g));
+    b = fmaxf(0.0f, fminf(1.0f, b));
+    a = fmaxf(0.0f, fminf(1.0f, a));
+    int ri = (int)(r * 255.0f), gi = (int)(g * 255.0f), bi = (int)(b * 255.0f), ai = (int)(a * 255.0f);
+    return ((uint32_t)ai << 24) | ((uint32_t)bi << 16) | ((uint32_t)gi << 8) | (uint32_t)ri;
+}
+
+struct BenchmarkParams {
+    const float4 *cells;
+    const float *sh_rows;
+    const uint32_t *start; // one element
+    uint32_t *out;
+    CameraParams cam;
+    uint32_t blocks_x;
+    float weight_threshold;
+    uint32_t max_steps;
+};
+
+template <int DEG, typename Faces>
+__global__ void __launch_bounds__(kBlock) benchmark_kernel(const BenchmarkParams p, const Faces fa) {
+    uint32_t r;
+    if (!thread_ray(p.cam.width * p.cam.height, p.cam.width, p.blocks_x, r))
+        return;
+    uint32_t pi = r % p.cam.width, pj = r / p.cam.width;
+    RayGeom ray;
+    cast_ray(p.cam, (int)pi, (int)pj, ray);
+    float nrm = __fsqrt_rn(__fmaf_rn(ray.dx, ray.dx, __fmaf_rn(ray.dy, ray.dy, __fmul_rn(ray.dz, ray.dz))));
+    if (nrm < 0.1f) {
+        p.out[r] = 0;
+        return;
+    }
+    float sh[sh_dim(DEG)];
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    auto cell_fn = [&](uint32_t cell, const float4 &pc, float t0, float t1, const float4 &) -> bool {
+        float s = pc.w;
+        float r_ = 0.0f, g_ = 0.0f, b_ = 0.0f;
+        if (s > 1e-6f)
+            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cell * sh_row(DEG), sh, r_, g_, b_);
+        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+        float alpha = 1.0f - expf(-s * delta);
+        float w = __fmul_rn(T, alpha);
+        cr = __fmaf_rn(w, r_, cr);
+        cg = __fmaf_rn(w, g_, cg);
+        cb = __fmaf_rn(w, b_, cb);
+        T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        return T > p.weight_threshold;
+    };
+    walk(fa, p.cells, ray, __ldg(p.start), p.max_steps, cell_fn);
+    p.out[r] = pack_rgba8(cr, cg, cb, 1.0f);
+}
+
+} // namespace rfb

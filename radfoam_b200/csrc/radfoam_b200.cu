@@ -1,0 +1,487 @@
+// C-ABI implementation (include/radfoam_b200.h) of the B200 foam tracer.
+// Host side: argument checks, cached scene re-layout, kernel dispatch.
+#include "../../include/radfoam_b200.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "foam_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local uint64_t g_launches = 0;
+
+int fail(const std::string &msg) {
+    g_last_error = msg;
+    return 1;
+}
+
+#define RFB_CUDA(call)                                                                    \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(std::string("CUDA call failed at " __FILE__ ":") +                \
+                        std::to_string(__LINE__) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+#define RFB_LAUNCHED()                                                                    \
+    do {                                                                                  \
+        ++g_launches;                                                                     \
+        RFB_CUDA(cudaGetLastError());                                                     \
+    } while (0)
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    // grow-only; reallocation synchronises, steady state does not
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes)
+            return cudaSuccess;
+        if (ptr) {
+            cudaError_t e = cudaFree(ptr);
+            ptr = nullptr;
+            bytes = 0;
+            if (e != cudaSuccess)
+                return e;
+        }
+        size_t want = need + need / 16 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess)
+            bytes = want;
+        return e;
+    }
+    void release() {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+struct SceneKey {
+    const void *points = nullptr, *attrs = nullptr, *adj = nullptr, *off = nullptr;
+    uint32_t n = 0, e = 0;
+    uint64_t version = 0;
+    bool faces = false;
+    bool operator==(const SceneKey &o) const {
+        return points == o.points && attrs == o.attrs && adj == o.adj && off == o.off && n == o.n &&
+               e == o.e && version == o.version;
+    }
+};
+
+int grid_for(uint64_t work_items, int block, int max_blocks = 148 * 16) {
+    uint64_t b = (work_items + block - 1) / block;
+    if (b > (uint64_t)max_blocks)
+        b = max_blocks;
+    if (b < 1)
+        b = 1;
+    return (int)b;
+}
+
+} // namespace
+
+struct rfb_pipeline {
+    int sh_degree;
+    int attr_dtype;
+    int device = -1;
+    DeviceBuffer cells, sh_rows, faces, nbr, acc;
+    SceneKey key;
+    bool key_valid = false;
+    uint32_t acc_points = 0;
+};
+
+namespace {
+
+using namespace rfb;
+
+int check_device(rfb_pipeline *p) {
+    int dev = 0;
+    RFB_CUDA(cudaGetDevice(&dev));
+    if (p->device < 0)
+        p->device = dev;
+    else if (p->device != dev)
+        return fail("pipeline was first used on CUDA device " + std::to_string(p->device) +
+                    " but the current device is " + std::to_string(dev) +
+                    " (create one pipeline per device)");
+    return 0;
+}
+
+// (Re)build the internal mirrors of the scene unless the caller vouches they are current.
+int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *attrs, uint32_t e,
+                 const uint32_t *adj, const uint32_t *off, bool need_faces,
+                 const rfb_launch_opts *opts, cudaStream_t stream) {
+    if (int rc = check_device(p))
+        return rc;
+    SceneKey k;
+    k.points = points;
+    k.attrs = attrs;
+    k.adj = adj;
+    k.off = off;
+    k.n = n;
+    k.e = e;
+    k.version = opts ? opts->scene_version : 0;
+    if (p->key_valid && k.version != 0 && k == p->key && (p->key.faces || !need_faces))
+        return 0;
+    p->key_valid = false;
+
+    const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
+    RFB_CUDA(p->cells.ensure((size_t)n * sizeof(float4)));
+    RFB_CUDA(p->sh_rows.ensure((size_t)n * SR * sizeof(float)));
+    if (n) {
+        int grid = grid_for((uint64_t)n * SR, 256);
+        if (p->attr_dtype == RFB_FLOAT16)
+            build_cells_kernel<__half><<<grid, 256, 0, stream>>>(
+                points, reinterpret_cast<const __half *>(attrs), n, A, SR,
+                reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+        else
+            build_cells_kernel<float><<<grid, 256, 0, stream>>>(
+                points, reinterpret_cast<const float *>(attrs), n, A, SR,
+                reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+        RFB_LAUNCHED();
+    }
+    if (need_faces) {
+        size_t slots = (size_t)e + n + 2 + 32; // padded rows + over-read tail
+        RFB_CUDA(p->faces.ensure(slots * sizeof(uint2)));
+        RFB_CUDA(p->nbr.ensure(slots * sizeof(uint32_t)));
+        RFB_CUDA(cudaMemsetAsync(p->faces.ptr, 0, slots * sizeof(uint2), stream));
+        if (n) {
+            build_faces_kernel<<<grid_for((uint64_t)n * 16, 256), 256, 0, stream>>>(
+                points, n, adj, off, reinterpret_cast<uint2 *>(p->faces.ptr),
+                reinterpret_cast<uint32_t *>(p->nbr.ptr));
+            RFB_LAUNCHED();
+        }
+    }
+    k.faces = need_faces;
+    p->key = k;
+    p->key_valid = true;
+    return 0;
+}
+
+void ray_grid(uint32_t num_rays, uint32_t image_width, uint32_t &blocks, uint32_t &blocks_x,
+              uint32_t &width_used) {
+    width_used = (image_width && num_rays % image_width == 0) ? image_width : 0;
+    if (width_used) {
+        uint32_t h = num_rays / width_used;
+        blocks_x = (width_used + 15) / 16;
+        blocks = blocks_x * ((h + 7) / 8);
+    } else {
+        blocks_x = 0;
+        blocks = (num_rays + kBlock - 1) / kBlock;
+    }
+}
+
+template <typename Faces>
+int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t blocks,
+                   cudaStream_t stream) {
+    switch (deg) {
+    case 0: forward_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
+    case 1: forward_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
+    case 2: forward_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
+    default: forward_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
+    }
+    RFB_LAUNCHED();
+    return 0;
+}
+
+template <typename Faces>
+int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
+                    cudaStream_t stream) {
+    switch (deg) {
+    case 0: backward_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    case 1: backward_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    case 2: backward_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    default: backward_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    }
+    RFB_LAUNCHED();
+    return 0;
+}
+
+template <typename Faces>
+int launch_benchmark(int deg, const BenchmarkParams &bp, const Faces &fa, uint32_t blocks,
+                     cudaStream_t stream) {
+    switch (deg) {
+    case 0: benchmark_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    case 1: benchmark_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    case 2: benchmark_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    default: benchmark_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    }
+    RFB_LAUNCHED();
+    return 0;
+}
+
+rfb_trace_settings settings_or_default(const rfb_trace_settings *s) {
+    rfb_trace_settings d;
+    d.weight_threshold = 0.001f; // default_trace_settings(), pipeline.h:15-20
+    d.max_intersections = 1024;
+    return s ? *s : d;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *rfb_last_error(void) { return g_last_error.c_str(); }
+int rfb_abi_version(void) { return RFB_ABI_VERSION; }
+uint64_t rfb_launch_count(void) { return g_launches; }
+void rfb_reset_launch_count(void) { g_launches = 0; }
+
+int rfb_create_pipeline(int sh_degree, int attr_dtype, rfb_pipeline **out) {
+    if (!out)
+        return fail("rfb_create_pipeline: out is NULL");
+    *out = nullptr;
+    if (attr_dtype != RFB_FLOAT32 && attr_dtype != RFB_FLOAT16)
+        return fail("Unsupported attribute type");
+    if (sh_degree < 0 || sh_degree > 3)
+        return fail("Unsupported SH degree");
+    rfb_pipeline *p = new (std::nothrow) rfb_pipeline();
+    if (!p)
+        return fail("out of host memory");
+    p->sh_degree = sh_degree;
+    p->attr_dtype = attr_dtype;
+    *out = p;
+    return 0;
+}
+
+void rfb_destroy_pipeline(rfb_pipeline *p) {
+    if (!p)
+        return;
+    p->cells.release();
+    p->sh_rows.release();
+    p->faces.release();
+    p->nbr.release();
+    p->acc.release();
+    delete p;
+}
+
+uint32_t rfb_attribute_dim(const rfb_pipeline *p) { return p ? (uint32_t)rfb::attr_dim(p->sh_degree) : 0; }
+int rfb_attribute_type(const rfb_pipeline *p) { return p ? p->attr_dtype : -1; }
+uint32_t rfb_grad_row_floats(const rfb_pipeline *p) { return p ? (uint32_t)rfb::grad_row(p->sh_degree) : 0; }
+void rfb_invalidate_cache(rfb_pipeline *p) {
+    if (p)
+        p->key_valid = false;
+}
+
+int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points, uint32_t point_adjacency_size,
+                               const uint32_t *point_adjacency, const uint32_t *point_adjacency_offsets,
+                               void *adjacent_diff, void *stream) {
+    (void)point_adjacency_size;
+    if (num_points == 0)
+        return 0;
+    if (!points || !point_adjacency || !point_adjacency_offsets || !adjacent_diff)
+        return fail("rfb_prefetch_adjacent_diff: NULL argument");
+    rfb::adjacent_diff_kernel<<<grid_for((uint64_t)num_points * 16, 256), 256, 0, (cudaStream_t)stream>>>(
+        points, num_points, point_adjacency, point_adjacency_offsets,
+        reinterpret_cast<uint2 *>(adjacent_diff));
+    RFB_LAUNCHED();
+    return 0;
+}
+
+int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint32_t num_points,
+                      const float *points, const void *attributes, uint32_t point_adjacency_size,
+                      const uint32_t *point_adjacency, const uint32_t *point_adjacency_offsets,
+                      uint32_t num_rays, const float *rays, const uint32_t *start_point_index,
+                      uint32_t num_depth_quantiles, const float *depth_quantiles, void *ray_rgba,
+                      float *quantile_depths, uint32_t *quantile_point_indices,
+                      uint32_t *num_intersections, void *point_contribution,
+                      const rfb_launch_opts *opts, void *stream_) {
+    if (!p)
+        return fail("rfb_trace_forward: pipeline is NULL");
+    if (num_rays == 0)
+        return 0;
+    if (!points || !attributes || !point_adjacency || !point_adjacency_offsets || !rays ||
+        !start_point_index || !ray_rgba)
+        return fail("rfb_trace_forward: NULL argument");
+    if (depth_quantiles && num_depth_quantiles && (!quantile_depths || !quantile_point_indices))
+        return fail("rfb_trace_forward: depth_quantiles given without output buffers");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (int rc = ensure_scene(p, num_points, points, attributes, point_adjacency_size, point_adjacency,
+                              point_adjacency_offsets, true, opts, stream))
+        return rc;
+    rfb_trace_settings s = settings_or_default(settings);
+    ForwardParams fp;
+    fp.cells = reinterpret_cast<const float4 *>(p->cells.ptr);
+    fp.sh_rows = reinterpret_cast<const float *>(p->sh_rows.ptr);
+    fp.rays = rays;
+    fp.start = start_point_index;
+    fp.quantiles = num_depth_quantiles ? depth_quantiles : nullptr;
+    fp.rgba = ray_rgba;
+    fp.qdepth = quantile_depths;
+    fp.qidx = quantile_point_indices;
+    fp.nint = num_intersections;
+    fp.contrib = point_contribution;
+    fp.num_rays = num_rays;
+    fp.num_q = num_depth_quantiles;
+    fp.weight_threshold = s.weight_threshold;
+    fp.max_steps = s.max_intersections;
+    fp.out_half = p->attr_dtype == RFB_FLOAT16;
+    uint32_t blocks;
+    ray_grid(num_rays, opts ? opts->image_width : 0, blocks, fp.blocks_x, fp.image_width);
+    PaddedFaces fa;
+    fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
+    fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
+    fa.off = point_adjacency_offsets;
+    return launch_forward(p->sh_degree, fp, fa, blocks, stream);
+}
+
+int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *settings,
+                                  uint32_t num_points, const float *points, const void *attributes,
+                                  uint32_t point_adjacency_size, const uint32_t *point_adjacency,
+                                  const uint32_t *point_adjacency_offsets, uint32_t num_rays,
+                                  const float *rays, const uint32_t *start_point_index,
+                                  uint32_t num_depth_quantiles, const float *depth_quantiles,
+                                  const uint32_t *quantile_point_indices, const void *ray_rgba,
+                                  const void *ray_rgba_grad, const float *depth_grad,
+                                  const void *ray_error, void *point_error,
+                                  const rfb_launch_opts *opts, void *stream_) {
+    if (!p)
+        return fail("rfb_trace_backward: pipeline is NULL");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (int rc = check_device(p))
+        return rc;
+    const int GR = grad_row(p->sh_degree);
+    size_t acc_bytes = (size_t)num_points * GR * sizeof(float);
+    RFB_CUDA(p->acc.ensure(acc_bytes));
+    RFB_CUDA(cudaMemsetAsync(p->acc.ptr, 0, acc_bytes, stream));
+    p->acc_points = num_points;
+    if (num_rays == 0)
+        return 0;
+    if (!points || !attributes || !point_adjacency || !point_adjacency_offsets || !rays ||
+        !start_point_index || !ray_rgba || !ray_rgba_grad)
+        return fail("rfb_trace_backward: NULL argument");
+    if (depth_quantiles && num_depth_quantiles && (!quantile_point_indices || !depth_grad))
+        return fail("depth_grad must be provided if depth_quantiles is provided");
+    if (int rc = ensure_scene(p, num_points, points, attributes, point_adjacency_size, point_adjacency,
+                              point_adjacency_offsets, true, opts, stream))
+        return rc;
+    rfb_trace_settings s = settings_or_default(settings);
+    BackwardParams bp;
+    bp.cells = reinterpret_cast<const float4 *>(p->cells.ptr);
+    bp.sh_rows = reinterpret_cast<const float *>(p->sh_rows.ptr);
+    bp.rays = rays;
+    bp.start = start_point_index;
+    bp.quantiles = num_depth_quantiles ? depth_quantiles : nullptr;
+    bp.qidx = quantile_point_indices;
+    bp.rgba = ray_rgba;
+    bp.rgba_grad = ray_rgba_grad;
+    bp.depth_grad = depth_grad;
+    bp.ray_error = ray_error;
+    bp.point_error = ray_error ? point_error : nullptr;
+    bp.acc = reinterpret_cast<float *>(p->acc.ptr);
+    bp.num_rays = num_rays;
+    bp.num_q = num_depth_quantiles;
+    bp.weight_threshold = s.weight_threshold;
+    bp.max_steps = s.max_intersections;
+    bp.io_half = p->attr_dtype == RFB_FLOAT16;
+    uint32_t blocks;
+    ray_grid(num_rays, opts ? opts->image_width : 0, blocks, bp.blocks_x, bp.image_width);
+    PaddedFaces fa;
+    fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
+    fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
+    fa.off = point_adjacency_offsets;
+    return launch_backward(p->sh_degree, bp, fa, blocks, stream);
+}
+
+int rfb_grad_accumulator(rfb_pipeline *p, float **ptr, uint64_t *num_floats) {
+    if (!p || !ptr || !num_floats)
+        return fail("rfb_grad_accumulator: NULL argument");
+    *ptr = reinterpret_cast<float *>(p->acc.ptr);
+    *num_floats = (uint64_t)p->acc_points * grad_row(p->sh_degree);
+    return 0;
+}
+
+int rfb_trace_backward_finalize(rfb_pipeline *p, uint32_t num_points, float *points_grad,
+                                void *attribute_grad, uint32_t flags, void *stream_) {
+    if (!p)
+        return fail("rfb_trace_backward_finalize: pipeline is NULL");
+    if (num_points == 0)
+        return 0;
+    if (!points_grad || !attribute_grad)
+        return fail("rfb_trace_backward_finalize: NULL argument");
+    if (num_points != p->acc_points)
+        return fail("rfb_trace_backward_finalize: no accumulated gradients for this point count");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
+    int grid = grid_for((uint64_t)num_points * A, 256);
+    int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
+    if (p->attr_dtype == RFB_FLOAT16)
+        finalize_grads_kernel<__half><<<grid, 256, 0, stream>>>(
+            reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
+            reinterpret_cast<__half *>(attribute_grad), scrub);
+    else
+        finalize_grads_kernel<float><<<grid, 256, 0, stream>>>(
+            reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
+            reinterpret_cast<float *>(attribute_grad), scrub);
+    RFB_LAUNCHED();
+    return 0;
+}
+
+int rfb_trace_backward(rfb_pipeline *p, const rfb_trace_settings *settings, uint32_t num_points,
+                       const float *points, const void *attributes, uint32_t point_adjacency_size,
+                       const uint32_t *point_adjacency, const uint32_t *point_adjacency_offsets,
+                       uint32_t num_rays, const float *rays, const uint32_t *start_point_index,
+                       uint32_t num_depth_quantiles, const float *depth_quantiles,
+                       const uint32_t *quantile_point_indices, const void *ray_rgba,
+                       const void *ray_rgba_grad, const float *depth_grad, const void *ray_error,
+                       float *ray_grad, float *points_grad, void *attribute_grad, void *point_error,
+                       const rfb_launch_opts *opts, void *stream) {
+    (void)ray_grad; // never written, like the reference kernel
+    if (int rc = rfb_trace_backward_accumulate(
+            p, settings, num_points, points, attributes, point_adjacency_size, point_adjacency,
+            point_adjacency_offsets, num_rays, rays, start_point_index, num_depth_quantiles,
+            depth_quantiles, quantile_point_indices, ray_rgba, ray_rgba_grad, depth_grad, ray_error,
+            point_error, opts, stream))
+        return rc;
+    return rfb_trace_backward_finalize(p, num_points, points_grad, attribute_grad,
+                                       opts ? opts->flags : 0, stream);
+}
+
+int rfb_trace_benchmark(rfb_pipeline *p, const rfb_trace_settings *settings, uint32_t num_points,
+                        const float *points, const void *attributes, const uint32_t *point_adjacency,
+                        const uint32_t *point_adjacency_offsets, const void *adjacent_diff,
+                        const rfb_camera *camera, const uint32_t *start_point_index,
+                        uint32_t *output_rgba, const rfb_launch_opts *opts, void *stream_) {
+    if (!p)
+        return fail("rfb_trace_benchmark: pipeline is NULL");
+    if (!points || !attributes || !point_adjacency || !point_adjacency_offsets || !adjacent_diff ||
+        !camera || !start_point_index || !output_rgba)
+        return fail("rfb_trace_benchmark: NULL argument");
+    if (camera->model != RFB_PINHOLE && camera->model != RFB_FISHEYE)
+        return fail("Invalid camera model");
+    if (camera->width == 0 || camera->height == 0)
+        return 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (int rc = ensure_scene(p, num_points, points, attributes, 0, point_adjacency,
+                              point_adjacency_offsets, false, opts, stream))
+        return rc;
+    rfb_trace_settings s = settings_or_default(settings);
+    BenchmarkParams bp;
+    bp.cells = reinterpret_cast<const float4 *>(p->cells.ptr);
+    bp.sh_rows = reinterpret_cast<const float *>(p->sh_rows.ptr);
+    bp.start = start_point_index;
+    bp.out = output_rgba;
+    memcpy(bp.cam.position, camera->position, sizeof(float) * 3);
+    memcpy(bp.cam.forward, camera->forward, sizeof(float) * 3);
+    memcpy(bp.cam.right, camera->right, sizeof(float) * 3);
+    memcpy(bp.cam.up, camera->up, sizeof(float) * 3);
+    bp.cam.fov = camera->fov;
+    bp.cam.width = camera->width;
+    bp.cam.height = camera->height;
+    bp.cam.model = camera->model;
+    bp.weight_threshold = s.weight_threshold;
+    bp.max_steps = s.max_intersections;
+    bp.blocks_x = (camera->width + 15) / 16;
+    uint32_t blocks = bp.blocks_x * ((camera->height + 7) / 8);
+    CallerFaces fa;
+    fa.faces = reinterpret_cast<const uint2 *>(adjacent_diff);
+    fa.adj = point_adjacency;
+    fa.off = point_adjacency_offsets;
+    return launch_benchmark(p->sh_degree, bp, fa, blocks, stream);
+}
+
+} // extern "C"

@@ -1,0 +1,477 @@
+"""Host-side mirror of radfoam's pipeline bindings for the tracing hot path.
+
+Same names, keyword arguments, result-dict keys, dtypes, shapes and validation
+errors as the pybind11 module the reference's Python code calls
+(torch_bindings/pipeline_bindings.cpp:107-672), so
+``radfoam_model/render.py::TraceRays`` runs unmodified against a ``Pipeline`` from
+here.  PyTorch is used for device memory and streams only; the work happens in the
+hand-written sm_100a kernels behind the C ABI (include/radfoam_b200.h), called
+through ctypes with raw device pointers.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import torch
+
+from . import _lib
+
+_DTYPES = {
+    "float32": torch.float32, "float": torch.float32, torch.float32: torch.float32,
+    "float16": torch.float16, "half": torch.float16, torch.float16: torch.float16,
+}
+_DTYPE_NAMES = {torch.float32: "float32", torch.float16: "float16", torch.float64: "float64",
+                torch.uint32: "uint32", torch.int32: "int32", torch.int64: "int64"}
+
+
+def _dtype_name(dt) -> str:
+    return _DTYPE_NAMES.get(dt, str(dt).replace("torch.", ""))
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+class Pipeline:
+    """radfoam::Pipeline (src/tracing/pipeline.h:58-131) for one (sh_degree, dtype)."""
+
+    def __init__(self, sh_degree: int, attr_dtype):
+        if isinstance(attr_dtype, str) or isinstance(attr_dtype, torch.dtype):
+            if attr_dtype not in _DTYPES:
+                # dtype_to_scalar_type() accepts more names, create_pipeline() then rejects them
+                raise RuntimeError("Unsupported attribute type")
+            dt = _DTYPES[attr_dtype]
+        else:
+            raise RuntimeError("dtype must be a string or torch.dtype")
+        self._lib = _lib.load()
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.rfb_create_pipeline(int(sh_degree), 1 if dt == torch.float16 else 0,
+                                                 ctypes.byref(handle)))
+        self._handle = handle
+        self._dtype = dt
+        self._sh_degree = int(sh_degree)
+        self._attr_dim = int(self._lib.rfb_attribute_dim(handle))
+        # scene-mirror cache bookkeeping: identity + torch version counters of the four
+        # scene tensors last traced; a match means the device-side mirrors are current.
+        self.cache_scene = True
+        self._scene_refs = None
+        self._scene_version = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.rfb_destroy_pipeline(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # --- reference API -------------------------------------------------------------
+    def attribute_dim(self) -> int:
+        return self._attr_dim
+
+    def attribute_type(self):
+        return self._dtype
+
+    @property
+    def sh_degree(self) -> int:
+        return self._sh_degree
+
+    def grad_row_floats(self) -> int:
+        return int(self._lib.rfb_grad_row_floats(self._handle))
+
+    def invalidate_cache(self) -> None:
+        self._scene_refs = None
+        self._lib.rfb_invalidate_cache(self._handle)
+
+    # validate_scene_data(), pipeline_bindings.cpp:8-71
+    def _validate_scene(self, points, attributes, point_adjacency, point_adjacency_offsets):
+        if points.size(-1) != 3:
+            raise RuntimeError(f"points had dimension {points.size(-1)} along axis -1, expected 3")
+        if points.dtype != torch.float32:
+            raise RuntimeError(f"points had dtype {_dtype_name(points.dtype)}, expected float32")
+        if points.device.type != "cuda":
+            raise RuntimeError("points must be on CUDA device")
+        num_points = points.numel() // 3
+        if attributes.size(-1) != self._attr_dim:
+            raise RuntimeError(f"attributes had dimension {attributes.size(-1)} along axis -1, "
+                               f"expected {self._attr_dim}")
+        if attributes.numel() // self._attr_dim != num_points:
+            raise RuntimeError("attributes must have the same number of rows as points")
+        if attributes.dtype != self._dtype:
+            raise RuntimeError(f"attributes had dtype {_dtype_name(attributes.dtype)}, "
+                               f"expected {_dtype_name(self._dtype)}")
+        if attributes.device.type != "cuda":
+            raise RuntimeError("attributes must be on CUDA device")
+        if point_adjacency_offsets.dtype != torch.uint32:
+            raise RuntimeError("point_adjacency_offsets must have uint32 dtype")
+        if point_adjacency_offsets.device.type != "cuda":
+            raise RuntimeError("point_adjacency_offsets must be on CUDA device")
+        if point_adjacency_offsets.numel() != num_points + 1:
+            raise RuntimeError("point_adjacency_offsets must have num_points + 1 elements")
+        if point_adjacency.dtype != torch.uint32:
+            raise RuntimeError("point_adjacency must have uint32 dtype")
+        if point_adjacency.device.type != "cuda":
+            raise RuntimeError("point_adjacency must be on CUDA device")
+
+    @staticmethod
+    def _validate_rays(rays, start_point, num_rays):
+        if rays.size(-1) != 6:
+            raise RuntimeError("rays must have 6 as the last dimension")
+        if rays.dtype != torch.float32:
+            raise RuntimeError("rays must have float32 dtype")
+        if rays.device.type != "cuda":
+            raise RuntimeError("rays must be on CUDA device")
+        if start_point.numel() != num_rays:
+            raise RuntimeError("start_point must have the same batch size as rays")
+        if start_point.dtype != torch.uint32:
+            raise RuntimeError("start_point must have uint32 dtype")
+        if start_point.device.type != "cuda":
+            raise RuntimeError("start_point must be on CUDA device")
+
+    def _settings(self, weight_threshold, max_intersections):
+        s = _lib.TraceSettings(0.001, 1024)  # default_trace_settings(), pipeline.h:15-20
+        if weight_threshold is not None:
+            s.weight_threshold = float(weight_threshold)
+        if max_intersections is not None:
+            s.max_intersections = int(max_intersections)
+        return s
+
+    def _opts(self, scene, rays, flags=0):
+        """Launch hints: scene-mirror reuse key and the image-tiling width."""
+        version = 0
+        if self.cache_scene:
+            refs = self._scene_refs
+            same = (refs is not None and all(r() is t and v == t._version
+                                             for (r, v), t in zip(refs, scene)))
+            if not same:
+                self._scene_version += 1
+                self._scene_refs = [(weakref.ref(t), t._version) for t in scene]
+            version = self._scene_version
+        width = int(rays.shape[-2]) if rays is not None and rays.dim() >= 3 else 0
+        return _lib.LaunchOpts(version, width, flags)
+
+    # trace_forward(), pipeline_bindings.cpp:107-265
+    def trace_forward(self, points, attributes, point_adjacency, point_adjacency_offsets, rays,
+                      start_point, depth_quantiles=None, weight_threshold=None,
+                      max_intersections=None, return_contribution=False):
+        points_c = points.contiguous()
+        attributes_c = attributes.contiguous()
+        adj_c = point_adjacency.contiguous()
+        off_c = point_adjacency_offsets.contiguous()
+        rays_c = rays.contiguous()
+        start_c = start_point.contiguous()
+        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
+
+        return_depth = depth_quantiles is not None
+        num_points = points_c.size(0)
+        num_rays = rays_c.numel() // 6
+        self._validate_rays(rays_c, start_c, num_rays)
+
+        num_q = 0
+        dq_c = None
+        if return_depth:
+            dq_c = depth_quantiles.contiguous()
+            num_q = dq_c.size(-1)
+            if dq_c.dtype != torch.float32:
+                raise RuntimeError("depth_quantiles must have float32 dtype")
+            if dq_c.device.type != "cuda":
+                raise RuntimeError("depth_quantiles must be on CUDA device")
+            if num_q == 0 or dq_c.numel() // num_q != num_rays:
+                raise RuntimeError("depth_quantiles must have the same batch size as rays")
+
+        settings = self._settings(weight_threshold, max_intersections)
+        dev = rays_c.device
+        batch = list(rays_c.shape[:-1])
+        rgba = torch.empty(batch + [4], dtype=self._dtype, device=dev)
+        num_intersections = torch.empty(batch + [1], dtype=torch.uint32, device=dev)
+        contribution = None
+        if return_contribution:
+            contribution = torch.zeros((num_points, 1), dtype=self._dtype, device=dev)
+        depth = depth_indices = None
+        if return_depth:
+            depth = torch.empty(batch + [num_q], dtype=torch.float32, device=dev)
+            depth_indices = torch.empty(batch + [num_q], dtype=torch.uint32, device=dev)
+
+        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._lib.rfb_trace_forward(
+                self._handle, ctypes.byref(settings), num_points, _ptr(points_c), _ptr(attributes_c),
+                adj_c.numel(), _ptr(adj_c), _ptr(off_c), num_rays, _ptr(rays_c), _ptr(start_c),
+                num_q, _ptr(dq_c), _ptr(rgba), _ptr(depth), _ptr(depth_indices),
+                _ptr(num_intersections), _ptr(contribution), ctypes.byref(opts), stream))
+
+        out = {"rgba": rgba}
+        if return_depth:
+            out["depth"] = depth
+            out["depth_indices"] = depth_indices
+        if return_contribution:
+            out["contribution"] = contribution
+        out["num_intersections"] = num_intersections
+        return out
+
+    def _backward_args(self, points, attributes, point_adjacency, point_adjacency_offsets, rays,
+                       start_point, rgb_out, grad_in, depth_quantiles, depth_indices,
+                       depth_grad_in, ray_error):
+        """Shared validation of trace_backward (pipeline_bindings.cpp:267-439)."""
+        points_c = points.contiguous()
+        attributes_c = attributes.contiguous()
+        adj_c = point_adjacency.contiguous()
+        off_c = point_adjacency_offsets.contiguous()
+        rays_c = rays.contiguous()
+        start_c = start_point.contiguous()
+        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
+        num_rays = rays_c.numel() // 6
+        self._validate_rays(rays_c, start_c, num_rays)
+
+        grad_c = grad_in.contiguous()
+        if grad_c.size(-1) != 4:
+            raise RuntimeError("rgb_grad_in must have 4 as the last dimension")
+        if grad_c.dtype != self._dtype:
+            raise RuntimeError(f"rgb_grad_in had dtype {_dtype_name(grad_c.dtype)}, "
+                               f"expected {_dtype_name(self._dtype)}")
+        if grad_c.device.type != "cuda":
+            raise RuntimeError("rgb_grad_in must be on CUDA device")
+        if grad_c.numel() // 4 != num_rays:
+            raise RuntimeError("rgb_grad_in must have the same batch size as rays")
+        # the reference passes rgb_out.data_ptr() unchecked (pipeline_bindings.cpp:477); a
+        # non-contiguous or wrong-dtype tensor would be read as garbage there, so reject it
+        rgb_c = rgb_out.contiguous()
+        if rgb_c.dtype != self._dtype or rgb_c.numel() != 4 * num_rays or rgb_c.device.type != "cuda":
+            raise RuntimeError("rgb_out must be the [..., 4] rgba tensor trace_forward returned")
+
+        num_q = 0
+        dq_c = di_c = dg_c = None
+        if depth_quantiles is not None:
+            dq_c = depth_quantiles.contiguous()
+            num_q = dq_c.size(-1)
+            if dq_c.dtype != torch.float32:
+                raise RuntimeError("depth_quantiles must have float32 dtype")
+            if dq_c.device.type != "cuda":
+                raise RuntimeError("depth_quantiles must be on CUDA device")
+            if dq_c.numel() != num_rays * num_q:
+                raise RuntimeError("depth_quantiles must have the same batch size as rays")
+            if depth_grad_in is None:
+                raise RuntimeError("depth_grad must be provided if depth_quantiles is provided")
+            if depth_indices is None:
+                raise RuntimeError("depth_indices must be provided if depth_quantiles is provided")
+            di_c = depth_indices.contiguous()
+            if di_c.dtype != torch.uint32:
+                raise RuntimeError("depth_indices must have uint32 dtype")
+            if di_c.device.type != "cuda":
+                raise RuntimeError("depth_indices must be on CUDA device")
+            if di_c.numel() != num_rays * num_q:
+                raise RuntimeError("depth_indices must have the same batch size as rays")
+            dg_c = depth_grad_in.contiguous()
+            if dg_c.size(-1) != num_q:
+                raise RuntimeError("depth_grad must have the same number of depth quantiles as "
+                                   "depth_quantiles")
+            if dg_c.dtype != torch.float32:
+                raise RuntimeError(f"depth_grad had dtype {_dtype_name(dg_c.dtype)}, expected float32")
+            if dg_c.device.type != "cuda":
+                raise RuntimeError("depth_grad must be on CUDA device")
+            if dg_c.numel() != num_rays * num_q:
+                raise RuntimeError("depth_grad must have the same batch size as rays")
+
+        err_c = None
+        if ray_error is not None:
+            err_c = ray_error.contiguous()
+            if err_c.dtype != self._dtype:
+                raise RuntimeError(f"ray_error had dtype {_dtype_name(err_c.dtype)}, "
+                                   f"expected {_dtype_name(self._dtype)}")
+            if err_c.device.type != "cuda":
+                raise RuntimeError("ray_error must be on CUDA device")
+            if err_c.numel() != num_rays:
+                raise RuntimeError("ray_error must have the same batch size as rays")
+        return (points_c, attributes_c, adj_c, off_c, rays_c, start_c, rgb_c, grad_c, dq_c, di_c,
+                dg_c, err_c, num_rays, num_q)
+
+    # trace_backward(), pipeline_bindings.cpp:267-497
+    def trace_backward(self, points, attributes, point_adjacency, point_adjacency_offsets, rays,
+                       start_point, rgb_out, grad_in, depth_quantiles=None, depth_indices=None,
+                       depth_grad_in=None, ray_error=None, weight_threshold=None,
+                       max_intersections=None, scrub_nonfinite=False):
+        """``scrub_nonfinite`` (extension, default off) zeroes non-finite gradient
+        entries inside the kernel epilogue, saving the two masked passes
+        radfoam_model/render.py:98-99 makes after this call."""
+        (points_c, attributes_c, adj_c, off_c, rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c,
+         err_c, num_rays, num_q) = self._backward_args(
+            points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out,
+            grad_in, depth_quantiles, depth_indices, depth_grad_in, ray_error)
+        num_points = points_c.size(0)
+        dev = rays_c.device
+        settings = self._settings(weight_threshold, max_intersections)
+        # fully overwritten by the kernels' epilogue: no zero-fill pass needed
+        attr_grad = torch.empty((attributes_c.size(0), self._attr_dim), dtype=self._dtype, device=dev)
+        points_grad = torch.empty((num_points, 3), dtype=torch.float32, device=dev)
+        ray_grad = torch.empty_like(rays_c)  # never written, like the reference
+        point_error = None
+        if err_c is not None:
+            point_error = torch.zeros((num_points, 1), dtype=self._dtype, device=dev)
+
+        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c,
+                          _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._lib.rfb_trace_backward(
+                self._handle, ctypes.byref(settings), num_points, _ptr(points_c), _ptr(attributes_c),
+                adj_c.numel(), _ptr(adj_c), _ptr(off_c), num_rays, _ptr(rays_c), _ptr(start_c),
+                num_q, _ptr(dq_c), _ptr(di_c), _ptr(rgb_c), _ptr(grad_c), _ptr(dg_c), _ptr(err_c),
+                _ptr(ray_grad), _ptr(points_grad), _ptr(attr_grad), _ptr(point_error),
+                ctypes.byref(opts), stream))
+
+        out = {"points_grad": points_grad, "attr_grad": attr_grad, "ray_grad": ray_grad}
+        if err_c is not None:
+            out["point_error"] = point_error
+        return out
+
+    # ---- split backward (ray-sharded multi-GPU) ---------------------
+    def trace_backward_accumulate(self, points, attributes, point_adjacency,
+                                  point_adjacency_offsets, rays, start_point, rgb_out, grad_in,
+                                  depth_quantiles=None, depth_indices=None, depth_grad_in=None,
+                                  ray_error=None, weight_threshold=None, max_intersections=None):
+        """Backward into the pipeline's fp32 accumulator; returns it as a
+        ``[N, grad_row_floats]`` tensor VIEW (valid until the next call) so a
+        data-parallel caller can all-reduce it before ``trace_backward_finalize``."""
+        (points_c, attributes_c, adj_c, off_c, rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c,
+         err_c, num_rays, num_q) = self._backward_args(
+            points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out,
+            grad_in, depth_quantiles, depth_indices, depth_grad_in, ray_error)
+        num_points = points_c.size(0)
+        dev = rays_c.device
+        settings = self._settings(weight_threshold, max_intersections)
+        point_error = None
+        if err_c is not None:
+            point_error = torch.zeros((num_points, 1), dtype=self._dtype, device=dev)
+        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._lib.rfb_trace_backward_accumulate(
+                self._handle, ctypes.byref(settings), num_points, _ptr(points_c), _ptr(attributes_c),
+                adj_c.numel(), _ptr(adj_c), _ptr(off_c), num_rays, _ptr(rays_c), _ptr(start_c),
+                num_q, _ptr(dq_c), _ptr(di_c), _ptr(rgb_c), _ptr(grad_c), _ptr(dg_c), _ptr(err_c),
+                _ptr(point_error), ctypes.byref(opts), stream))
+        return self.grad_accumulator(dev), point_error
+
+    def grad_accumulator(self, device):
+        ptr = ctypes.c_void_p()
+        count = ctypes.c_uint64()
+        _lib.check(self._lib.rfb_grad_accumulator(self._handle, ctypes.byref(ptr), ctypes.byref(count)))
+        row = self.grad_row_floats()
+        n = count.value // row
+        if n == 0:
+            return torch.empty((0, row), dtype=torch.float32, device=device)
+        return _wrap_device_memory(ptr.value, (n, row), device)
+
+    def trace_backward_finalize(self, num_points, device, scrub_nonfinite=False):
+        attr_grad = torch.empty((num_points, self._attr_dim), dtype=self._dtype, device=device)
+        points_grad = torch.empty((num_points, 3), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(self._lib.rfb_trace_backward_finalize(
+                self._handle, num_points, _ptr(points_grad), _ptr(attr_grad),
+                _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, stream))
+        return points_grad, attr_grad
+
+    # trace_benchmark(), pipeline_bindings.cpp:499-585
+    def trace_benchmark(self, points, attributes, point_adjacency, point_adjacency_offsets,
+                        adjacent_diff, camera, start_point, output_rgba, weight_threshold=None,
+                        max_intersections=None):
+        points_c = points.contiguous()
+        attributes_c = attributes.contiguous()
+        adj_c = point_adjacency.contiguous()
+        off_c = point_adjacency_offsets.contiguous()
+        diff_c = adjacent_diff.contiguous()
+        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
+        num_points = points_c.size(0)
+
+        cam = _lib.Camera()
+        for key in ("position", "forward", "up", "right"):
+            vec = camera[key]
+            vals = [float(v) for v in (vec.detach().cpu().reshape(-1).tolist()
+                                       if isinstance(vec, torch.Tensor) else list(vec))]
+            getattr(cam, key)[:] = vals[:3]
+        cam.fov = float(camera["fov"])
+        cam.width = int(camera["width"])
+        cam.height = int(camera["height"])
+        model = camera["model"]
+        if model == "pinhole":
+            cam.model = 0
+        elif model == "fisheye":
+            cam.model = 1
+        else:
+            raise RuntimeError("Invalid camera model")
+
+        if start_point.numel() != 1:
+            raise RuntimeError("start_point must have a single element")
+        if start_point.dtype != torch.uint32:
+            raise RuntimeError("start_point must have uint32 dtype")
+        if start_point.device.type != "cuda":
+            raise RuntimeError("start_point must be on CUDA device")
+        if output_rgba.numel() != cam.width * cam.height:
+            raise RuntimeError("output_rgba must have width * height elements")
+        if output_rgba.dtype != torch.uint32:
+            raise RuntimeError("output_rgba must have uint32 dtype")
+        if output_rgba.device.type != "cuda":
+            raise RuntimeError("output_rgba must be on CUDA device")
+        if not output_rgba.is_contiguous():
+            raise RuntimeError("output_rgba must be contiguous")
+        if diff_c.numel() * diff_c.element_size() < 8 * adj_c.numel():
+            raise RuntimeError("adjacent_diff must hold one half4 per adjacency entry")
+
+        settings = self._settings(weight_threshold, max_intersections)
+        dev = points_c.device
+        opts = self._opts((points_c, attributes_c, adj_c, off_c), None)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._lib.rfb_trace_benchmark(
+                self._handle, ctypes.byref(settings), num_points, _ptr(points_c), _ptr(attributes_c),
+                _ptr(adj_c), _ptr(off_c), _ptr(diff_c), ctypes.byref(cam), _ptr(start_point),
+                _ptr(output_rgba), ctypes.byref(opts), stream))
+        return None
+
+    # radfoam::prefetch_adjacent_diff (pipeline.h:50-56); handy for trace_benchmark callers
+    def prefetch_adjacent_diff(self, points, point_adjacency, point_adjacency_offsets):
+        points_c = points.contiguous()
+        adj_c = point_adjacency.contiguous()
+        off_c = point_adjacency_offsets.contiguous()
+        out = torch.empty((adj_c.numel(), 4), dtype=torch.float16, device=points_c.device)
+        with torch.cuda.device(points_c.device):
+            stream = torch.cuda.current_stream(points_c.device).cuda_stream
+            _lib.check(self._lib.rfb_prefetch_adjacent_diff(
+                _ptr(points_c), points_c.size(0), adj_c.numel(), _ptr(adj_c), _ptr(off_c), _ptr(out),
+                stream))
+        return out
+
+
+def _wrap_device_memory(ptr: int, shape, device) -> torch.Tensor:
+    """Zero-copy float32 tensor over library-owned device memory."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    n = 1
+    for s in shape:
+        n *= int(s)
+    h.__cuda_array_interface__ = {
+        "shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+    }
+    t = torch.as_tensor(h, device=device)
+    return t.view(*shape)
+
+
+def create_pipeline(sh_degree, attr_dtype="float32") -> Pipeline:
+    """radfoam.create_pipeline (pipeline_bindings.cpp:587-590, 669-672)."""
+    if not isinstance(sh_degree, int) or sh_degree < 0 or sh_degree > 3:
+        raise RuntimeError("Unsupported SH degree")
+    return Pipeline(sh_degree, attr_dtype)
+
+
+def launch_count() -> int:
+    return int(_lib.load().rfb_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().rfb_reset_launch_count()

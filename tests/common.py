@@ -1,0 +1,93 @@
+"""Shared seeded test cases (numpy) and comparison helpers."""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from radfoam_b200 import foam
+
+NONE = 0xFFFFFFFF
+
+
+class Case:
+    """One traced scene: foam + rays + start cells + quantiles + upstream gradients."""
+
+    def __init__(self, f: foam.Foam, rays, start, quantiles, seed=1):
+        self.foam = f
+        self.rays = rays
+        self.start = start
+        self.quantiles = quantiles
+        rng = np.random.default_rng(seed)
+        batch = rays.shape[:-1]
+        self.grad_rgba = rng.normal(size=batch + (4,)).astype(np.float32)
+        q = 0 if quantiles is None else quantiles.shape[-1]
+        self.grad_depth = (rng.normal(size=batch + (q,)) * 1e-4).astype(np.float32) if q else None
+
+
+def _quantiles(batch, q, seed):
+    if q == 0:
+        return None
+    rng = np.random.default_rng(seed)
+    # training passes sorted-descending uniform quantiles (train.py:176-180)
+    return np.sort(rng.uniform(0.05, 0.95, size=batch + (q,)).astype(np.float32), axis=-1)[..., ::-1].copy()
+
+
+@functools.lru_cache(maxsize=None)
+def config1(sh_degree: int = 3, q: int = 2, fixed_quantiles: bool = True) -> Case:
+    """BASELINE config 1: 256-point foam, 32x32 pinhole camera at (0,0,-3), fov 0.7,
+    quantiles (0.7, 0.3)."""
+    f = foam.small_foam(256, sh_degree=sh_degree, seed=0)
+    rays = foam.pinhole_rays(32, 32, (0, 0, -3), fov=0.7, up=(0, 1, 0))
+    start = np.full((32, 32), foam.nearest_point(f.points, (0, 0, -3)), dtype=np.uint32)
+    if q == 0:
+        dq = None
+    elif fixed_quantiles and q == 2:
+        dq = np.tile(np.array([0.7, 0.3], dtype=np.float32), (32, 32, 1))
+    else:
+        dq = _quantiles((32, 32), q, 7)
+    return Case(f, rays, start, dq)
+
+
+@functools.lru_cache(maxsize=None)
+def scene_case(num_points: int = 20000, width: int = 160, height: int = 96, q: int = 2,
+               sh_degree: int = 3, inside: bool = False) -> Case:
+    """Mid-size shell scene (SURVEY.md §8d recipe) seen from outside (or inside) the shell."""
+    f = foam.scene_foam(num_points, sh_degree=sh_degree)
+    pos = (0.3, 0.3, 0.3) if inside else (2.5, 2.5, 2.5)
+    target = (1.0, 0.2, -0.1) if inside else (0.0, 0.0, 0.0)
+    rays = foam.pinhole_rays(width, height, pos, target=target, fov=0.9)
+    start = np.full((height, width), foam.nearest_point(f.points, pos), dtype=np.uint32)
+    return Case(f, rays, start, _quantiles((height, width), q, 11))
+
+
+@functools.lru_cache(maxsize=None)
+def random_ray_case(num_points: int = 20000, num_rays: int = 20000, cameras: int = 16, q: int = 2) -> Case:
+    """Unordered ray batch from several cameras, per-ray start cells: the access pattern of
+    the reference's training batches (train.py:61, scene.py:224-234)."""
+    f = foam.scene_foam(num_points)
+    rng = np.random.default_rng(5)
+    cams = rng.normal(size=(cameras, 3))
+    cams = 2.5 * cams / np.linalg.norm(cams, axis=1, keepdims=True)
+    starts = np.array([foam.nearest_point(f.points, c) for c in cams], dtype=np.uint32)
+    which = rng.integers(0, cameras, size=num_rays)
+    target = rng.normal(0.0, 0.4, size=(num_rays, 3))
+    d = target - cams[which]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([cams[which], d], axis=1).astype(np.float32)
+    return Case(f, rays, starts[which].copy(), _quantiles((num_rays,), q, 13))
+
+
+def grad_error(got: np.ndarray, ref: np.ndarray) -> float:
+    """max |got - ref| / max |ref| over entries finite in the reference (the reference zeroes
+    non-finite gradient entries afterwards, render.py:98-99).  Gradients are float scatter-adds
+    whose order differs run to run in the reference itself, hence a norm-scaled figure."""
+    ref = ref.astype(np.float64)
+    got = got.astype(np.float64)
+    ok = np.isfinite(ref) & np.isfinite(got)
+    scale = max(float(np.abs(ref[ok]).max()) if ok.any() else 0.0, 1e-30)
+    return float(np.abs(got[ok] - ref[ok]).max() / scale) if ok.any() else 0.0
+
+
+def nonfinite_mismatch(got: np.ndarray, ref: np.ndarray) -> int:
+    return int((np.isfinite(got) != np.isfinite(ref)).sum())
