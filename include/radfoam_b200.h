@@ -185,6 +185,13 @@ void rfb_reset_launch_count(void);
 /* drop cached scene mirrors (next call rebuilds) */
 void rfb_invalidate_cache(rfb_pipeline *pipeline);
 
+/* Live kernel timing for roofline reporting: when enabled, CUDA events are recorded on the
+ * launching stream right around the forward / backward ray kernel of every call.
+ * rfb_last_kernel_ms(which = 0 forward, 1 backward) waits for and returns the duration of the
+ * most recent one. */
+void rfb_set_profiling(rfb_pipeline *pipeline, int enabled);
+int rfb_last_kernel_ms(rfb_pipeline *pipeline, int which, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

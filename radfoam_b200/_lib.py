@@ -61,6 +61,8 @@ SIGNATURES = {
     "rfb_launch_count": (c_uint64, []),
     "rfb_reset_launch_count": (None, []),
     "rfb_invalidate_cache": (None, [_P]),
+    "rfb_set_profiling": (None, [_P, c_int]),
+    "rfb_last_kernel_ms": (c_int, [_P, c_int, POINTER(c_float)]),
 }
 
 _lib = None

@@ -94,6 +94,10 @@ struct rfb_pipeline {
     SceneKey key;
     bool key_valid = false;
     uint32_t acc_points = 0;
+    // optional live kernel timing (rfb_set_profiling): events around the ray kernels
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // fwd start/stop, bwd start/stop
+    bool ev_valid[2] = {false, false};
 };
 
 namespace {
@@ -176,6 +180,17 @@ void ray_grid(uint32_t num_rays, uint32_t image_width, uint32_t &blocks, uint32_
     }
 }
 
+int profile_mark(rfb_pipeline *p, int which, cudaStream_t stream) {
+    if (!p->profiling)
+        return 0;
+    if (!p->ev[which])
+        RFB_CUDA(cudaEventCreate(&p->ev[which]));
+    RFB_CUDA(cudaEventRecord(p->ev[which], stream));
+    if (which & 1)
+        p->ev_valid[which >> 1] = true;
+    return 0;
+}
+
 template <typename Faces>
 int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t blocks,
                    cudaStream_t stream) {
@@ -256,6 +271,9 @@ void rfb_destroy_pipeline(rfb_pipeline *p) {
     p->faces.release();
     p->nbr.release();
     p->acc.release();
+    for (auto &e : p->ev)
+        if (e)
+            cudaEventDestroy(e);
     delete p;
 }
 
@@ -265,6 +283,23 @@ uint32_t rfb_grad_row_floats(const rfb_pipeline *p) { return p ? (uint32_t)rfb::
 void rfb_invalidate_cache(rfb_pipeline *p) {
     if (p)
         p->key_valid = false;
+}
+
+void rfb_set_profiling(rfb_pipeline *p, int enabled) {
+    if (p) {
+        p->profiling = enabled != 0;
+        p->ev_valid[0] = p->ev_valid[1] = false;
+    }
+}
+
+int rfb_last_kernel_ms(rfb_pipeline *p, int which, float *ms) {
+    if (!p || !ms || which < 0 || which > 1)
+        return fail("rfb_last_kernel_ms: bad argument");
+    if (!p->ev_valid[which])
+        return fail("rfb_last_kernel_ms: no timed launch recorded (enable rfb_set_profiling first)");
+    RFB_CUDA(cudaEventSynchronize(p->ev[2 * which + 1]));
+    RFB_CUDA(cudaEventElapsedTime(ms, p->ev[2 * which], p->ev[2 * which + 1]));
+    return 0;
 }
 
 int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points, uint32_t point_adjacency_size,
@@ -326,7 +361,11 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
     fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
     fa.off = point_adjacency_offsets;
-    return launch_forward(p->sh_degree, fp, fa, blocks, stream);
+    if (int rc = profile_mark(p, 0, stream))
+        return rc;
+    if (int rc = launch_forward(p->sh_degree, fp, fa, blocks, stream))
+        return rc;
+    return profile_mark(p, 1, stream);
 }
 
 int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *settings,
@@ -384,7 +423,11 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
     fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
     fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
     fa.off = point_adjacency_offsets;
-    return launch_backward(p->sh_degree, bp, fa, blocks, stream);
+    if (int rc = profile_mark(p, 2, stream))
+        return rc;
+    if (int rc = launch_backward(p->sh_degree, bp, fa, blocks, stream))
+        return rc;
+    return profile_mark(p, 3, stream);
 }
 
 int rfb_grad_accumulator(rfb_pipeline *p, float **ptr, uint64_t *num_floats) {

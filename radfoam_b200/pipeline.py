@@ -80,6 +80,16 @@ class Pipeline:
     def grad_row_floats(self) -> int:
         return int(self._lib.rfb_grad_row_floats(self._handle))
 
+    def set_profiling(self, enabled: bool) -> None:
+        """Record CUDA events around the ray kernels (for roofline reporting)."""
+        self._lib.rfb_set_profiling(self._handle, 1 if enabled else 0)
+
+    def last_kernel_ms(self, which: str) -> float:
+        ms = ctypes.c_float()
+        _lib.check(self._lib.rfb_last_kernel_ms(self._handle, {"forward": 0, "backward": 1}[which],
+                                                ctypes.byref(ms)))
+        return float(ms.value)
+
     def invalidate_cache(self) -> None:
         self._scene_refs = None
         self._lib.rfb_invalidate_cache(self._handle)

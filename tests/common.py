@@ -91,3 +91,41 @@ def grad_error(got: np.ndarray, ref: np.ndarray) -> float:
 
 def nonfinite_mismatch(got: np.ndarray, ref: np.ndarray) -> int:
     return int((np.isfinite(got) != np.isfinite(ref)).sum())
+
+
+# ---- comparison bars -----------------------------------------------------------------------
+# Against the reference's own kernels (same libdevice expf/logf) the bar is the north star's:
+# integers bit-exact, floats 1e-5, gradients 1e-5 of max|ref|.  Against the CPU restatement the
+# integer traversal is still bit-exact, but composited floats go through libm's expf/logf
+# instead of the GPU's MUFU-based ones (a few 1e-7 relative apart), and two formulas of the
+# reference amplify that: alpha = 1 - exp(-x) loses x's relative accuracy for small x, and the
+# quantile depth t0 + log(T/q)/sigma divides an O(1e-7) difference in T by the cell's density.
+# The CPU-side bars below state that conditioning explicitly instead of hiding it in a loose
+# global tolerance.
+CPU_GRAD_TOL = 3e-4
+
+
+def depth_tolerance(attributes: np.ndarray, depth: np.ndarray, depth_indices: np.ndarray) -> np.ndarray:
+    """Per-entry bound for |depth - ref| when expf/logf implementations differ:
+    1e-5 * max(1, |depth|) + 2e-6 / sigma(cell that crossed the quantile)."""
+    idx = depth_indices.astype(np.int64)
+    valid = depth_indices != NONE
+    sigma = np.ones(depth.shape, dtype=np.float64)
+    sigma[valid] = np.maximum(attributes[idx[valid], -1].astype(np.float64), 1e-30)
+    return 1e-5 * np.maximum(1.0, np.abs(depth)) + np.where(valid, 2e-6 / sigma, 0.0)
+
+
+def assert_forward_close_cpu(got: dict, ref: dict, attributes: np.ndarray) -> None:
+    """CUDA path (or golden reference output) vs the CPU restatement."""
+    assert np.array_equal(got["num_intersections"], ref["num_intersections"]), "num_intersections"
+    np.testing.assert_allclose(got["rgba"].astype(np.float32), ref["rgba"].astype(np.float32),
+                               rtol=1e-5, atol=1e-5)
+    if "depth_indices" in ref:
+        assert np.array_equal(got["depth_indices"], ref["depth_indices"]), "depth_indices"
+        tol = depth_tolerance(attributes, ref["depth"], ref["depth_indices"])
+        bad = np.abs(got["depth"].astype(np.float64) - ref["depth"]) > tol
+        assert not bad.any(), f"{int(bad.sum())} depth entries outside the conditioned bound"
+    if "contribution" in ref and "contribution" in got:
+        # a float scatter-add like the gradients: norm-scaled
+        assert grad_error(got["contribution"].astype(np.float32),
+                          ref["contribution"].astype(np.float32)) <= 1e-5

@@ -1,0 +1,74 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU and
+exports every symbol include/radfoam_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import common  # noqa: F401  (sets up sys.path via conftest)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "radfoam_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rfb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_entry_points():
+    syms = header_symbols()
+    for needed in ("rfb_create_pipeline", "rfb_trace_forward", "rfb_trace_backward",
+                   "rfb_trace_benchmark", "rfb_prefetch_adjacent_diff", "rfb_attribute_dim",
+                   "rfb_attribute_type", "rfb_last_error"):
+        assert needed in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from radfoam_b200 import _lib
+
+    lib = ctypes.CDLL(_lib.library_path())
+    for name in header_symbols():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+
+
+def test_pipeline_lifecycle_without_gpu():
+    from radfoam_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.rfb_abi_version() == 1
+    for deg, dim in ((0, 4), (1, 13), (2, 28), (3, 49)):
+        for dtype in (0, 1):
+            h = ctypes.c_void_p()
+            assert lib.rfb_create_pipeline(deg, dtype, ctypes.byref(h)) == 0
+            assert lib.rfb_attribute_dim(h) == dim  # pipeline.cu:767-769
+            assert lib.rfb_attribute_type(h) == dtype
+            assert lib.rfb_grad_row_floats(h) == ((3 * (deg + 1) ** 2 + 3) // 4) * 4 + 4
+            lib.rfb_destroy_pipeline(h)
+    h = ctypes.c_void_p()
+    assert lib.rfb_create_pipeline(4, 0, ctypes.byref(h)) != 0
+    assert b"Unsupported SH degree" in lib.rfb_last_error()
+    assert lib.rfb_create_pipeline(3, 7, ctypes.byref(h)) != 0
+    assert b"Unsupported attribute type" in lib.rfb_last_error()
+
+
+def test_missing_library_is_a_hard_error(monkeypatch):
+    from radfoam_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_LIB_NAME", "libdoes_not_exist.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "radfoam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/_ref", "").lower() or f == "__init__.py" and False, \
+                    f"{f} mentions the oracle"

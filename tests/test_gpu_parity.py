@@ -112,6 +112,13 @@ def assert_forward_equal(got, ref, exact_floats=False):
         assert np.array_equal(got["rgba"], ref["rgba"]), "rgba not bit-identical"
 
 
+def assert_matches_cpu_oracle(got, ref, case, grads=True):
+    """Integers bit-exact; floats to the conditioning-aware CPU bars of tests/common.py."""
+    common.assert_forward_close_cpu(got, ref, case.foam.attributes)
+    if grads:
+        assert_grads_close(got, ref, common.CPU_GRAD_TOL)
+
+
 def assert_grads_close(got, ref, tol=GRAD_TOL):
     for k in ("points_grad", "attr_grad"):
         err = common.grad_error(got[k], ref[k])
@@ -125,28 +132,25 @@ def test_config1_matches_cpu_oracle(torch_cuda, deg, q):
     case = common.config1(deg, q)
     got = run_ours(torch_cuda, case, return_contribution=True)
     ref = run_cpu_oracle(case, return_contribution=True)
-    assert_forward_equal(got, ref)
-    np.testing.assert_allclose(got["contribution"], ref["contribution"], rtol=1e-5, atol=1e-6)
-    assert_grads_close(got, ref)
+    assert_matches_cpu_oracle(got, ref, case)
 
 
 def test_random_quantiles_three(torch_cuda):
     case = common.config1(3, 3, fixed_quantiles=False)
-    assert_forward_equal(run_ours(torch_cuda, case, backward=False), run_cpu_oracle(case, backward=False))
+    assert_matches_cpu_oracle(run_ours(torch_cuda, case, backward=False), run_cpu_oracle(case, backward=False),
+                              case, grads=False)
 
 
 def test_scene_matches_cpu_oracle(torch_cuda):
     case = common.scene_case()
     got, ref = run_ours(torch_cuda, case), run_cpu_oracle(case)
-    assert_forward_equal(got, ref)
-    assert_grads_close(got, ref)
+    assert_matches_cpu_oracle(got, ref, case)
 
 
 def test_random_ray_batch_matches_cpu_oracle(torch_cuda):
     case = common.random_ray_case()
     got, ref = run_ours(torch_cuda, case), run_cpu_oracle(case)
-    assert_forward_equal(got, ref)
-    assert_grads_close(got, ref)
+    assert_matches_cpu_oracle(got, ref, case)
 
 
 @pytest.mark.parametrize("kwargs", [dict(max_intersections=1), dict(max_intersections=7),
@@ -157,8 +161,7 @@ def test_trace_settings(torch_cuda, kwargs):
     full.update(kwargs)
     got = run_ours(torch_cuda, case, **kwargs)
     ref = run_cpu_oracle(case, **full)
-    assert_forward_equal(got, ref)
-    assert_grads_close(got, ref)
+    assert_matches_cpu_oracle(got, ref, case)
     assert got["num_intersections"].max() <= full["max_intersections"] + 1
 
 
@@ -217,8 +220,7 @@ def test_cpu_oracle_matches_reference_kernels(torch_cuda):
     """Pins the restatement (and the Eigen shim) against the reference source itself."""
     case = common.scene_case(num_points=60000, width=320, height=200)
     ref, cpu = run_ref_gpu(torch_cuda, case), run_cpu_oracle(case)
-    assert_forward_equal(cpu, ref)
-    assert_grads_close(cpu, ref)
+    assert_matches_cpu_oracle(cpu, ref, case)
 
 
 def test_half_attributes_forward(torch_cuda):
@@ -345,7 +347,7 @@ def test_autograd_op_and_scrub(torch_cuda):
     for got, want in ((pts.grad, ref["points_grad"]), (attrs.grad, ref["attr_grad"])):
         assert torch.isfinite(got).all()
         want = np.where(np.isfinite(want), want, 0.0)
-        assert common.grad_error(got.cpu().numpy(), want) < 1e-5
+        assert common.grad_error(got.cpu().numpy(), want) < common.CPU_GRAD_TOL
 
 
 def test_empty_ray_batch(torch_cuda):
