@@ -25,10 +25,17 @@ __host__ __device__ constexpr int sh_row(int deg) { return (3 * sh_dim(deg) + 3)
 __host__ __device__ constexpr int grad_row(int deg) { return sh_row(deg) + 4; }
 __host__ __device__ constexpr int attr_dim(int deg) { return 1 + 3 * sh_dim(deg); }
 
-// first slot of row `i` in the padded face arrays: even (16-byte aligned rows),
-// rows never overlap, at most one slack slot per row, no prefix scan needed.
+// Padded face rows: row i starts at padded_begin() -- a multiple of 4 slots (32-byte
+// aligned) -- and holds nf real faces followed by ZERO faces up to the next multiple of 4
+// (a zero face has dp == 0, which never wins), so the scan works on whole 4-face chunks
+// without index masking.  Closed form, no prefix scan: with a = off_i + 3 i,
+// ceil4(a + nf + 3) >= ceil4(a) + ceil4(nf), so rows never overlap; at most 3 slack slots
+// per row stay unused (never written, never read).
 __host__ __device__ __forceinline__ uint32_t padded_begin(uint32_t off_i, uint32_t i) {
-    return (off_i + i + 1u) & ~1u;
+    return (off_i + 3u * i + 3u) & ~3u;
+}
+__host__ __device__ __forceinline__ uint64_t padded_slots(uint32_t num_points, uint32_t num_edges) {
+    return (uint64_t)num_edges + 3ull * num_points + 8ull;
 }
 
 // ---------------------------------------------------------------- loads
@@ -141,6 +148,29 @@ __device__ __forceinline__ void walk_face(uint2 h, float px, float py, float pz,
     t = __fdiv_rn(num, dp);
 }
 
+// MUFU.RCP: 1-ulp reciprocal (inputs/outputs flushed), used only to RANK faces; the value
+// that is kept, t1, always comes from the IEEE division.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    // volatile: keeps the MUFU unconditional so the ranking loop stays branch-free
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Same plane test without the division: returns num and dp.
+__device__ __forceinline__ void walk_face_parts(uint2 h, float px, float py, float pz,
+                                                const RayGeom &ray, float &num, float &dp) {
+    __half2 hxy = *reinterpret_cast<__half2 *>(&h.x);
+    __half2 hzw = *reinterpret_cast<__half2 *>(&h.y);
+    float ox = __low2float(hxy), oy = __high2float(hxy), oz = __low2float(hzw);
+    float fx = __fmaf_rn(ox, 0.5f, px);
+    float fy = __fmaf_rn(oy, 0.5f, py);
+    float fz = __fmaf_rn(oz, 0.5f, pz);
+    dp = __fmaf_rn(ox, ray.dx, __fmaf_rn(oy, ray.dy, __fmul_rn(oz, ray.dz)));
+    num = __fmaf_rn(ox, __fsub_rn(fx, ray.ox),
+                    __fmaf_rn(oy, __fsub_rn(fy, ray.oy), __fmul_rn(oz, __fsub_rn(fz, ray.oz))));
+}
+
 // Scene views the walk reads.  Two face layouts:
 //  * PaddedFaces: this library's own mirror. Rows start at padded_begin() (even
 //    slot => 16-byte aligned), so two faces arrive per 128-bit load; the
@@ -157,22 +187,69 @@ struct PaddedFaces {
         begin = padded_begin(a, cell);
         nf = b - a;
     }
-    // first-minimum scan over the row: strict `<`, faces in array order
-    __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
-                                         const RayGeom &ray, float &t1, uint32_t &face) const {
+    // Exact scan: first minimum of t = num / dp (IEEE) over faces with dp > 0, strict `<`,
+    // array order -- literally the reference's loop (zero pad faces have dp == 0).
+    __device__ __forceinline__ void scan_exact(uint32_t begin, uint32_t nf, float px, float py,
+                                               float pz, const RayGeom &ray, float &t1,
+                                               uint32_t &face) const {
         const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
         for (uint32_t f = 0; f < nf; f += 4) {
             uint4 a = ldg4(p + (f >> 1));
-            uint4 b = ldg4(p + (f >> 1) + 1); // may over-read into the next row / tail pad
+            uint4 b = ldg4(p + (f >> 1) + 1);
             float t, dp;
             walk_face(make_uint2(a.x, a.y), px, py, pz, ray, t, dp);
             if (dp > 0.0f && t < t1) { t1 = t; face = f; }
             walk_face(make_uint2(a.z, a.w), px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1 && f + 1 < nf) { t1 = t; face = f + 1; }
+            if (dp > 0.0f && t < t1) { t1 = t; face = f + 1; }
             walk_face(make_uint2(b.x, b.y), px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1 && f + 2 < nf) { t1 = t; face = f + 2; }
+            if (dp > 0.0f && t < t1) { t1 = t; face = f + 2; }
             walk_face(make_uint2(b.z, b.w), px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1 && f + 3 < nf) { t1 = t; face = f + 3; }
+            if (dp > 0.0f && t < t1) { t1 = t; face = f + 3; }
+        }
+    }
+    // Fast scan with the same result.  Faces are RANKED by q = num * rcp(dp) (2 instructions
+    // instead of the ~10 of an IEEE division); q is within 2^-22 relative of the exact quotient,
+    // so if the runner-up's q clears the best q by more than 2^-19 relative, the exact
+    // quotients are ordered the same way and no exact tie exists: the winner is the
+    // reference's winner and t1 is its IEEE quotient.  Otherwise (near-ties, non-finite or
+    // flushed values: rare) the row is rescanned exactly.
+    __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
+                                         const RayGeom &ray, float &t1, uint32_t &face) const {
+        const float kInf = __int_as_float(0x7f800000);
+        const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
+        float best = kInf, second = kInf; // invariant: best <= second
+        uint32_t bf = kNone;
+        for (uint32_t f = 0; f < nf; f += 4) {
+            uint4 a = ldg4(p + (f >> 1));
+            uint4 b = ldg4(p + (f >> 1) + 1);
+            uint2 rec[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y),
+                            make_uint2(b.z, b.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float num, dp;
+                walk_face_parts(rec[k], px, py, pz, ray, num, dp);
+                float q = num * rcp_approx(dp);
+                q = (dp > 0.0f) ? q : kInf;
+                bf = (q < best) ? f + k : bf;
+                // runner-up: min(second, max(best, q)); a NaN q collapses it onto best, which
+                // only sends the row to the exact rescan
+                second = fminf(second, fmaxf(best, q));
+                best = fminf(best, q);
+            }
+        }
+        // 2^-19 relative clearance; |second| is capped at 4|best| because beyond that the gap
+        // itself dwarfs any rounding (and so that a lone candidate, second == +inf, is clear)
+        float ab = fabsf(best);
+        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
+        bool clear = (second - best) > margin; // false for NaN / no ranked face (inf - inf)
+        if (clear && fabsf(best) < 1e30f) {
+            // the winner's IEEE quotient: re-evaluate that one face exactly
+            float t, dp;
+            walk_face(ldg2(faces + begin + bf), px, py, pz, ray, t, dp);
+            t1 = t;
+            face = bf;
+        } else {
+            scan_exact(begin, nf, px, py, pz, ray, t1, face);
         }
     }
     __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {

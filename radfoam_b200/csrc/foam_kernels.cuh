@@ -46,15 +46,19 @@ __global__ void build_faces_kernel(const float *__restrict__ points, uint32_t nu
         uint32_t dst = padded_begin(a, i);
         float px = __ldg(points + 3 * (uint64_t)i), py = __ldg(points + 3 * (uint64_t)i + 1),
               pz = __ldg(points + 3 * (uint64_t)i + 2);
-        for (uint32_t f = lane; f < b - a; f += 16) {
-            uint32_t j = __ldg(adj + a + f);
-            float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
-                  qz = __ldg(points + 3 * (uint64_t)j + 2);
-            __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
-            __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
-            uint2 rec;
-            rec.x = *reinterpret_cast<uint32_t *>(&hxy);
-            rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+        uint32_t nf = b - a, nf4 = (nf + 3u) & ~3u;
+        for (uint32_t f = lane; f < nf4; f += 16) {
+            uint2 rec = make_uint2(0u, 0u); // pad: zero face, dp == 0 never wins
+            uint32_t j = 0;
+            if (f < nf) {
+                j = __ldg(adj + a + f);
+                float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
+                      qz = __ldg(points + 3 * (uint64_t)j + 2);
+                __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
+                __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
+                rec.x = *reinterpret_cast<uint32_t *>(&hxy);
+                rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+            }
             faces[dst + f] = rec;
             nbr[dst + f] = j;
         }
@@ -357,6 +361,291 @@ __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p
     };
 
     walk(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn);
+}
+
+// ------------------------------------------------------------------ backward, warp-aggregated
+// Same mathematics as backward_kernel; what changes is how the per-cell gradient rows reach
+// HBM.  Neighbouring rays of an 8x4 tile cross mostly the same cells, a few iterations apart
+// (one ray clips a sliver cell the other misses and they drift out of lock-step), so instead of
+// 13 x 128-bit reductions per lane per step the warp keeps a small direct-mapped cache of
+// gradient rows in shared memory:
+//   * every lane with a contribution writes its row (SH products + density grad) to a staging
+//     row in shared memory;
+//   * lanes are grouped by cell (MATCH.ANY); for each group the warp sums the staged rows
+//     "transposed" -- lane j owns elements 2j, 2j+1 of the row -- so the shared-memory update
+//     needs no atomics and has no bank conflicts, and adds the sum to the cell's cache row;
+//   * a cache row is written to HBM (13 lanes x one RED.128) only when its slot is claimed by
+//     another cell, or at the end of the warp's rays;
+//   * a lane that is alone in its cell skips all of that and issues its reductions directly,
+//     in parallel with the other singleton lanes.
+// Position gradients (3 floats to the previous composited cell) stay direct reductions.
+template <int DEG, typename Faces, int SLOTS>
+__global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardParams p, const Faces fa) {
+    constexpr int GR = grad_row(DEG);
+    constexpr int SR = sh_row(DEG);
+    constexpr int HALF_ROW = GR / 2; // lanes that own two row elements each
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(HALF_ROW <= 32, "row too wide for one warp pass");
+    static_assert((SLOTS & (SLOTS - 1)) == 0, "SLOTS must be a power of two");
+
+    extern __shared__ __align__(16) float smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WARP_FLOATS = 32 * GR + SLOTS * GR + SLOTS;
+    float *stage = smem + warp * WARP_FLOATS;       // [32][GR]
+    float *cache = stage + 32 * GR;                 // [SLOTS][GR]
+    uint32_t *tags = reinterpret_cast<uint32_t *>(cache + SLOTS * GR); // [SLOTS]
+    for (int i = lane; i < SLOTS; i += 32)
+        tags[i] = kNone;
+    __syncwarp();
+
+    uint32_t r;
+    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
+
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    float sh[sh_dim(DEG)];
+    float out[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, err = 0.0f;
+    uint32_t Q = 0, qi = 0;
+    const float *qv = nullptr, *dg = nullptr;
+    float cq = 0.0f, cdg = 0.0f;
+    uint32_t cur = 0;
+    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!done) {
+        const float *rp = p.rays + 6 * (uint64_t)r;
+        ray.ox = __ldg(rp + 0);
+        ray.oy = __ldg(rp + 1);
+        ray.oz = __ldg(rp + 2);
+        ray.dx = __ldg(rp + 3);
+        ray.dy = __ldg(rp + 4);
+        ray.dz = __ldg(rp + 5);
+        normalize_dir(ray.dx, ray.dy, ray.dz);
+        if (p.io_half) {
+            const __half *o = reinterpret_cast<const __half *>(p.rgba) + 4 * (uint64_t)r;
+            const __half *gg = reinterpret_cast<const __half *>(p.rgba_grad) + 4 * (uint64_t)r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                out[c] = __half2float(o[c]);
+                g[c] = __half2float(gg[c]);
+            }
+            if (p.ray_error)
+                err = __half2float(reinterpret_cast<const __half *>(p.ray_error)[r]);
+        } else {
+            float4 o = __ldg(reinterpret_cast<const float4 *>(p.rgba) + r);
+            float4 gg = __ldg(reinterpret_cast<const float4 *>(p.rgba_grad) + r);
+            out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
+            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+            if (p.ray_error)
+                err = __ldg(reinterpret_cast<const float *>(p.ray_error) + r);
+        }
+        Q = p.quantiles ? p.num_q : 0u;
+        qv = p.quantiles + (uint64_t)r * p.num_q;
+        dg = p.depth_grad + (uint64_t)r * p.num_q;
+        cq = Q ? __ldg(qv) : 0.0f;
+        for (uint32_t i = 0; i < Q; ++i) {
+            uint32_t pi = __ldg(p.qidx + (uint64_t)r * Q + i);
+            if (pi != kNone)
+                cdg += __ldg(dg + i) / ldg4(p.cells + pi).w;
+        }
+        cur = __ldg(p.start + r);
+        pc = ldg4(p.cells + cur);
+    }
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    uint32_t prev = kNone;
+    float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;
+    float pgx = 0.0f, pgy = 0.0f, pgz = 0.0f;
+    float cgx = 0.0f, cgy = 0.0f, cgz = 0.0f;
+    float t0 = 0.0f;
+    uint32_t n = 0;
+
+    for (;;) {
+        bool c_valid = false;   // this lane has a (SH, density) row for cell c_cell this iteration
+        bool c_sh = false;      // ... with a nonzero SH part
+        uint32_t c_cell = kNone;
+        float dL_ds = 0.0f;
+        float dL_drgb[3] = {0.0f, 0.0f, 0.0f};
+
+        if (!done) {
+            n++;
+            if (n > p.max_steps) {
+                done = true;
+            } else {
+                uint32_t begin, nf;
+                fa.row(cur, begin, nf);
+                float t1 = __int_as_float(0x7f800000);
+                uint32_t face = kNone;
+                fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                if (face == kNone) {
+                    done = true;
+                } else {
+                    uint32_t nxt = fa.neighbour(begin, face);
+                    float4 pn = ldg4(p.cells + nxt);
+                    if (t1 > t0) {
+                        float s = pc.w;
+                        float rgb[3] = {0.0f, 0.0f, 0.0f};
+                        if (s > 1e-6f)
+                            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * SR, sh, rgb[0], rgb[1], rgb[2]);
+                        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+                        float alpha = 1.0f - expf(-s * delta);
+                        float w = __fmul_rn(T, alpha);
+                        float one_m_alpha = __fsub_rn(1.0f, alpha);
+                        float dalpha_ds = delta * one_m_alpha;
+                        float dalpha_dd = (delta > 0.0f) ? s * one_m_alpha : 0.0f;
+                        cr = __fmaf_rn(w, rgb[0], cr);
+                        cg = __fmaf_rn(w, rgb[1], cg);
+                        cb = __fmaf_rn(w, rgb[2], cb);
+                        if (p.point_error) {
+                            if (p.io_half)
+                                atomicAdd(reinterpret_cast<__half *>(p.point_error) + cur, __float2half_rn(w * err));
+                            else
+                                atomicAdd(reinterpret_cast<float *>(p.point_error) + cur, w * err);
+                        }
+                        dL_drgb[0] = g[0] * w; dL_drgb[1] = g[1] * w; dL_drgb[2] = g[2] * w;
+                        float denom = T * (one_m_alpha + 1e-6f);
+                        float rest0 = (out[0] - cr) / denom, rest1 = (out[1] - cg) / denom, rest2 = (out[2] - cb) / denom;
+                        float dL_dalpha = T * ((rgb[0] - rest0) * g[0] + ((rgb[1] - rest1) * g[1] + (rgb[2] - rest2) * g[2]));
+                        dL_dalpha += (1.0f - out[3]) * g[3] / (one_m_alpha + 1e-6f);
+                        dL_ds = dL_dalpha * dalpha_ds;
+                        float dL_dd = dL_dalpha * dalpha_dd;
+                        float dL_dt0 = 0.0f;
+                        float Tn = __fmul_rn(T, one_m_alpha);
+                        while (qi < Q && Tn < cq) {
+                            float gq = __ldg(dg + qi) / s;
+                            dL_dt0 += gq;
+                            dL_ds += -gq * logf(__fdiv_rn(T, cq)) / s;
+                            cdg -= gq;
+                            qi++;
+                            if (qi < Q)
+                                cq = __ldg(qv + qi);
+                        }
+                        if (qi < Q) {
+                            dL_ds += -delta * cdg;
+                            dL_dd += -s * cdg;
+                        }
+                        dL_dt0 += -dL_dd;
+                        float dL_dt1 = dL_dd;
+                        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+                        if (prev != kNone)
+                            isect_grad(ppx, ppy, ppz, pc.x, pc.y, pc.z, ray, ax, ay, az);
+                        float bx, by, bz, ex, ey, ez, fx, fy, fz;
+                        isect_grad(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz);
+                        isect_grad(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez);
+                        isect_grad(pn.x, pn.y, pn.z, pc.x, pc.y, pc.z, ray, fx, fy, fz);
+                        pgx += dL_dt0 * ax; pgy += dL_dt0 * ay; pgz += dL_dt0 * az;
+                        cgx += dL_dt0 * ex + dL_dt1 * bx;
+                        cgy += dL_dt0 * ey + dL_dt1 * by;
+                        cgz += dL_dt0 * ez + dL_dt1 * bz;
+                        if (prev != kNone)
+                            red_add_v4(p.acc + (uint64_t)prev * GR + SR, 0.0f, pgx, pgy, pgz);
+                        ppx = pc.x; ppy = pc.y; ppz = pc.z;
+                        prev = cur;
+                        pgx = cgx; pgy = cgy; pgz = cgz;
+                        cgx = dL_dt1 * fx; cgy = dL_dt1 * fy; cgz = dL_dt1 * fz;
+                        T = Tn;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (rgb[c] == 0.0f)
+                                dL_drgb[c] = 0.0f;
+                        c_valid = true;
+                        c_cell = cur;
+                        c_sh = dL_drgb[0] != 0.0f || dL_drgb[1] != 0.0f || dL_drgb[2] != 0.0f;
+                        if (!(T > p.weight_threshold))
+                            done = true;
+                    }
+                    t0 = fmaxf(t0, t1);
+                    cur = nxt;
+                    pc = pn;
+                }
+            }
+        }
+
+        // ---- warp-collective phase: route this iteration's rows
+        unsigned grp = __match_any_sync(FULL, c_valid ? c_cell : (0x80000000u | lane));
+        bool single = c_valid && (grp & (grp - 1)) == 0;
+        bool staged = c_valid && !single;
+        if (single) {
+            float *row = p.acc + (uint64_t)c_cell * GR;
+            if (c_sh) {
+#pragma unroll
+                for (int i = 0; i < SR; i += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v[k] = (i + k < 3 * sh_dim(DEG)) ? sh[(i + k) / 3] * dL_drgb[(i + k) % 3] : 0.0f;
+                    red_add_v4(row + i, v[0], v[1], v[2], v[3]);
+                }
+            }
+            red_add_v4(row + SR, dL_ds, 0.0f, 0.0f, 0.0f);
+        }
+        unsigned todo = __ballot_sync(FULL, staged);
+        if (todo) {
+            if (staged) {
+                float4 *srow = reinterpret_cast<float4 *>(stage + lane * GR);
+#pragma unroll
+                for (int i = 0; i < SR; i += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v[k] = (i + k < 3 * sh_dim(DEG)) ? sh[(i + k) / 3] * dL_drgb[(i + k) % 3] : 0.0f;
+                    srow[i / 4] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                srow[SR / 4] = make_float4(dL_ds, 0.0f, 0.0f, 0.0f);
+            }
+            __syncwarp();
+            while (todo) {
+                int leader = __ffs(todo) - 1;
+                unsigned gmask = __shfl_sync(FULL, grp, leader);
+                uint32_t lc = __shfl_sync(FULL, c_cell, leader);
+                todo &= ~gmask;
+                float a0 = 0.0f, a1 = 0.0f;
+                if (lane < HALF_ROW) {
+                    unsigned m = gmask;
+                    while (m) {
+                        int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        float2 v = *reinterpret_cast<const float2 *>(stage + src * GR + 2 * lane);
+                        a0 += v.x;
+                        a1 += v.y;
+                    }
+                }
+                uint32_t slot = (lc * 2654435761u) >> (32 - __builtin_ctz(SLOTS));
+                uint32_t tag = tags[slot];
+                __syncwarp();
+                float2 *crow = reinterpret_cast<float2 *>(cache + slot * GR + 2 * lane);
+                if (tag == lc) {
+                    if (lane < HALF_ROW) {
+                        float2 c = *crow;
+                        c.x += a0;
+                        c.y += a1;
+                        *crow = c;
+                    }
+                } else {
+                    if (tag != kNone && lane < GR / 4) {
+                        float4 v = *reinterpret_cast<const float4 *>(cache + slot * GR + 4 * lane);
+                        red_add_v4(p.acc + (uint64_t)tag * GR + 4 * lane, v.x, v.y, v.z, v.w);
+                    }
+                    __syncwarp();
+                    if (lane < HALF_ROW)
+                        *crow = make_float2(a0, a1);
+                    if (lane == 0)
+                        tags[slot] = lc;
+                }
+                __syncwarp();
+            }
+        }
+        if (!__any_sync(FULL, !done))
+            break;
+    }
+
+    // drain the cache
+    __syncwarp();
+    for (int slot = 0; slot < SLOTS; ++slot) {
+        uint32_t tag = tags[slot];
+        if (tag != kNone && lane < GR / 4) {
+            float4 v = *reinterpret_cast<const float4 *>(cache + slot * GR + 4 * lane);
+            red_add_v4(p.acc + (uint64_t)tag * GR + 4 * lane, v.x, v.y, v.z, v.w);
+        }
+    }
 }
 
 // accumulator -> reference-layout gradient outputs (+ optional finite scrub)

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -150,10 +151,9 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
         RFB_LAUNCHED();
     }
     if (need_faces) {
-        size_t slots = (size_t)e + n + 2 + 32; // padded rows + over-read tail
+        size_t slots = (size_t)padded_slots(n, e); // rows padded to 4 faces, <= 3 slack per row
         RFB_CUDA(p->faces.ensure(slots * sizeof(uint2)));
         RFB_CUDA(p->nbr.ensure(slots * sizeof(uint32_t)));
-        RFB_CUDA(cudaMemsetAsync(p->faces.ptr, 0, slots * sizeof(uint2), stream));
         if (n) {
             build_faces_kernel<<<grid_for((uint64_t)n * 16, 256), 256, 0, stream>>>(
                 points, n, adj, off, reinterpret_cast<uint2 *>(p->faces.ptr),
@@ -215,6 +215,35 @@ int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t
     }
     RFB_LAUNCHED();
     return 0;
+}
+
+constexpr int kCacheSlots = 32;
+
+template <int DEG, typename Faces>
+int launch_backward_cached_deg(const BackwardParams &bp, const Faces &fa, uint32_t blocks,
+                               cudaStream_t stream) {
+    constexpr int GR = grad_row(DEG);
+    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * GR + kCacheSlots * GR + kCacheSlots) * sizeof(float);
+    static bool configured = false; // per template instantiation; idempotent attribute
+    if (!configured) {
+        RFB_CUDA(cudaFuncSetAttribute(backward_cached_kernel<DEG, Faces, kCacheSlots>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    backward_cached_kernel<DEG, Faces, kCacheSlots><<<blocks, kBlock, smem, stream>>>(bp, fa);
+    RFB_LAUNCHED();
+    return 0;
+}
+
+template <typename Faces>
+int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
+                           cudaStream_t stream) {
+    switch (deg) {
+    case 0: return launch_backward_cached_deg<0>(bp, fa, blocks, stream);
+    case 1: return launch_backward_cached_deg<1>(bp, fa, blocks, stream);
+    case 2: return launch_backward_cached_deg<2>(bp, fa, blocks, stream);
+    default: return launch_backward_cached_deg<3>(bp, fa, blocks, stream);
+    }
 }
 
 template <typename Faces>
@@ -425,7 +454,10 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
     fa.off = point_adjacency_offsets;
     if (int rc = profile_mark(p, 2, stream))
         return rc;
-    if (int rc = launch_backward(p->sh_degree, bp, fa, blocks, stream))
+    const char *mode = getenv("RFB_BWD_MODE"); // "direct" | "cached" (experiment switch)
+    bool cached = mode ? strcmp(mode, "direct") != 0 : true;
+    if (int rc = cached ? launch_backward_cached(p->sh_degree, bp, fa, blocks, stream)
+                        : launch_backward(p->sh_degree, bp, fa, blocks, stream))
         return rc;
     return profile_mark(p, 3, stream);
 }
