@@ -98,7 +98,7 @@ static void load_sh_as_rgb(int sh_dim, const float *coeffs, const void *attrs,
     for (int i = 0; i < 3 * sh_dim; ++i)
         rgb[i % 3] = fmaf(coeffs[i / 3], attr_at(attrs, is_half, base + i), rgb[i % 3]);
     for (int c = 0; c < 3; ++c)
-        rgb[c] = rgb[c] >= 0.0f ? rgb[c] : 0.0f; /* cwiseMax(0): NaN -> 0 like FSEL on GEU */
+        rgb[c] = (rgb[c] < 0.0f) ? 0.0f : rgb[c]; /* cwiseMax(0) as built: NaN stays NaN */
 }
 
 /* load_attributes lambda, src/tracing/pipeline.cu:47-55 */
@@ -164,16 +164,18 @@ static inline uint32_t scan_faces(const half_t *diff, uint32_t begin, uint32_t n
     return next_face;
 }
 
-/* cell_intersection_grad, src/tracing/tracing_utils.cuh:91-103 */
+/* cell_intersection_grad, src/tracing/tracing_utils.cuh:91-103, in the reference's SASS
+ * association: n = q - p; a = fma(p + q, 0.5, -o); dp = fma(nx,dx,fma(ny,dy,nz*dz));
+ * num = fma(nx,ax,fma(ny,ay,nz*az)); g_i = fma(num, d_i, dp*(o_i - p_i)) / (dp*dp). */
 static void cell_intersection_grad(const float p[3], const float q[3],
                                    const float o[3], const float d[3], float g[3]) {
-    float fo[3], fn[3];
+    float n[3], a[3];
     for (int i = 0; i < 3; ++i) {
-        fo[i] = (p[i] + q[i]) / 2.0f;
-        fn[i] = q[i] - p[i];
+        n[i] = q[i] - p[i];
+        a[i] = fmaf(p[i] + q[i], 0.5f, -o[i]);
     }
-    float num = fmaf(fo[0] - o[0], fn[0], fmaf(fo[1] - o[1], fn[1], (fo[2] - o[2]) * fn[2]));
-    float dp = fmaf(fn[0], d[0], fmaf(fn[1], d[1], fn[2] * d[2]));
+    float dp = fmaf(n[0], d[0], fmaf(n[1], d[1], n[2] * d[2]));
+    float num = fmaf(n[0], a[0], fmaf(n[1], a[1], n[2] * a[2]));
     float dp2 = dp * dp;
     for (int i = 0; i < 3; ++i)
         g[i] = fmaf(num, d[i], dp * (o[i] - p[i])) / dp2;
@@ -380,51 +382,48 @@ static void backward_ray(int sh_degree, int is_half, float weight_threshold,
         uint32_t nxt = adj[b + face];
         float Pn[3] = {points[3 * (size_t)nxt], points[3 * (size_t)nxt + 1], points[3 * (size_t)nxt + 2]};
         if (t1 > t0) {
-            /* cell functor, src/tracing/pipeline.cu:219-331 */
+            /* cell functor, src/tracing/pipeline.cu:219-331; multiply-adds associated as in
+             * the reference's sm_100 SASS (gradient sums cancel heavily, so a differently
+             * fused multiply-add is visible at 1e-4 of the result) */
             float rgb[3], s;
             load_attributes(sh_dim, sh, attrs, is_half, cur, rgb, &s);
             float delta = fmaxf(t1 - t0, 0.0f);
-            float alpha = 1.0f - expf(-s * delta);
-            float w = T * alpha;
-            float dalpha_ds = delta * (1.0f - alpha);
-            float dalpha_ddelta = 0.0f;
-            if (delta > 0.0f)
-                dalpha_ddelta = s * (1.0f - alpha);
+            float alpha = 1.0f - expf(s * -delta);
+            float oma = 1.0f - alpha;
+            float omae = oma + 1e-6f;
+            float denom = omae * T;
+            float w = alpha * T;
             for (int c = 0; c < 3; ++c)
                 acc[c] = fmaf(w, rgb[c], acc[c]);
             if (point_error)
                 add_attr(point_error, is_half, cur, w * error, parallel);
 
-            float dL_drgb[3], rest[3];
-            float denom = T * ((1.0f - alpha) + 1e-6f);
-            for (int c = 0; c < 3; ++c) {
-                dL_drgb[c] = rgba_grad[c] * w;
+            float rest[3];
+            for (int c = 0; c < 3; ++c)
                 rest[c] = (rgba[c] - acc[c]) / denom;
-            }
-            float dot = fmaf(rgb[0] - rest[0], rgba_grad[0],
-                             fmaf(rgb[1] - rest[1], rgba_grad[1], (rgb[2] - rest[2]) * rgba_grad[2]));
-            float dL_dalpha = T * dot;
-            dL_dalpha += (1.0f - rgba[3]) * rgba_grad[3] / ((1.0f - alpha) + 1e-6f);
-
-            float dL_ds = dL_dalpha * dalpha_ds;
-            float dL_ddelta = dL_dalpha * dalpha_ddelta;
+            float dot = fmaf(rgba_grad[0], rgb[0] - rest[0],
+                             fmaf(rgba_grad[1], rgb[1] - rest[1], rgba_grad[2] * (rgb[2] - rest[2])));
+            float k_alpha = (1.0f - rgba[3]) * rgba_grad[3];
+            float dL_dalpha = fmaf(dot, T, k_alpha / omae);
+            float Tn = oma * T;
+            float dL_ds = dL_dalpha * (delta * oma);
             float dL_dt0 = 0.0f;
-
-            float Tn = T * (1.0f - alpha);
             while (qi < Q && Tn < cq) {
                 float gq = depth_grad[qi] / s;
-                dL_dt0 += gq;
-                dL_ds += -gq * logf(T / cq) / s;
-                cdg -= gq;
+                dL_dt0 = gq + dL_dt0;
+                float m = logf(T / cq) * gq;
+                dL_ds = dL_ds - m / s;
+                cdg = cdg - gq;
                 qi++;
                 if (qi < Q)
                     cq = dq[qi];
             }
+            float dL_ddelta = dL_dalpha * ((delta > 0.0f) ? s * oma : 0.0f);
             if (qi < Q) {
-                dL_ds += -delta * cdg;
-                dL_ddelta += -s * cdg;
+                dL_ds = fmaf(cdg, -delta, dL_ds);
+                dL_ddelta = fmaf(cdg, -s, dL_ddelta);
             }
-            dL_dt0 += -dL_ddelta;
+            dL_dt0 = dL_dt0 - dL_ddelta;
             float dL_dt1 = dL_ddelta;
 
             float g_t0_prev[3] = {0, 0, 0}, g_t1_cur[3], g_t0_cur[3], g_t1_next[3];
@@ -434,9 +433,9 @@ static void backward_ray(int sh_degree, int is_half, float weight_threshold,
             cell_intersection_grad(P, prev_point, o, d, g_t0_cur);
             cell_intersection_grad(Pn, P, o, d, g_t1_next);
             for (int c = 0; c < 3; ++c) {
-                prev_grad[c] += dL_dt0 * g_t0_prev[c];
-                cur_grad[c] += fmaf(dL_dt0, g_t0_cur[c], dL_dt1 * g_t1_cur[c]);
-                next_grad[c] += dL_dt1 * g_t1_next[c];
+                prev_grad[c] = fmaf(dL_dt0, g_t0_prev[c], prev_grad[c]);
+                cur_grad[c] = cur_grad[c] + fmaf(dL_dt0, g_t0_cur[c], dL_dt1 * g_t1_cur[c]);
+                next_grad[c] = dL_dt1 * g_t1_next[c];
             }
             if (prev_idx != RF_NONE)
                 for (int c = 0; c < 3; ++c)
@@ -450,9 +449,9 @@ static void backward_ray(int sh_degree, int is_half, float weight_threshold,
             prev_idx = cur;
             T = Tn;
 
+            float dL_drgb[3];
             for (int c = 0; c < 3; ++c)
-                if (rgb[c] == 0.0f)
-                    dL_drgb[c] = 0.0f;
+                dL_drgb[c] = (rgb[c] == 0.0f) ? 0.0f : rgba_grad[c] * w;
             /* write_rgb_grad_to_sh, src/tracing/sh_utils.cuh:85-92 */
             for (int i = 0; i < 3 * sh_dim; ++i)
                 add_attr(attr_grad, is_half, cur * A + i, sh[i / 3] * dL_drgb[i % 3], parallel);

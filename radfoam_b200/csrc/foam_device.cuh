@@ -328,19 +328,137 @@ __device__ __forceinline__ uint32_t walk(const Faces &fa, const float4 *__restri
 }
 
 // d t / d p of the ray / bisector(p, q) intersection (cell_intersection_grad,
-// tracing_utils.cuh:91-103), from the fp32 points.
+// tracing_utils.cuh:91-103), from the fp32 points.  Gradient sums over rays cancel heavily
+// (terms 1e3x the result), so one differently-fused multiply-add shows up at 1e-4 of the
+// result; the association is therefore pinned to the reference's sm_100 SASS:
+//   n = q - p;  a = fma(p + q, 0.5, -o);  dp = fma(nx,dx, fma(ny,dy, nz*dz))
+//   num = fma(nx,ax, fma(ny,ay, nz*az));  g_i = fma(num, d_i, dp * (o_i - p_i)) / (dp * dp)
 __device__ __forceinline__ void isect_grad(float px, float py, float pz, float qx, float qy,
                                            float qz, const RayGeom &ray, float &gx, float &gy,
                                            float &gz) {
-    float fox = (px + qx) / 2.0f, foy = (py + qy) / 2.0f, foz = (pz + qz) / 2.0f;
-    float nx = qx - px, ny = qy - py, nz = qz - pz;
-    float num = (fox - ray.ox) * nx + ((foy - ray.oy) * ny + (foz - ray.oz) * nz);
-    float dp = nx * ray.dx + (ny * ray.dy + nz * ray.dz);
-    float inv = dp * dp;
-    gx = (num * ray.dx + dp * (ray.ox - px)) / inv;
-    gy = (num * ray.dy + dp * (ray.oy - py)) / inv;
-    gz = (num * ray.dz + dp * (ray.oz - pz)) / inv;
+    float nx = __fsub_rn(qx, px), ny = __fsub_rn(qy, py), nz = __fsub_rn(qz, pz);
+    float ax = __fmaf_rn(__fadd_rn(px, qx), 0.5f, -ray.ox);
+    float ay = __fmaf_rn(__fadd_rn(py, qy), 0.5f, -ray.oy);
+    float az = __fmaf_rn(__fadd_rn(pz, qz), 0.5f, -ray.oz);
+    float dp = __fmaf_rn(nx, ray.dx, __fmaf_rn(ny, ray.dy, __fmul_rn(nz, ray.dz)));
+    float num = __fmaf_rn(nx, ax, __fmaf_rn(ny, ay, __fmul_rn(nz, az)));
+    float inv = __fmul_rn(dp, dp);
+    gx = __fdiv_rn(__fmaf_rn(num, ray.dx, __fmul_rn(dp, __fsub_rn(ray.ox, px))), inv);
+    gy = __fdiv_rn(__fmaf_rn(num, ray.dy, __fmul_rn(dp, __fsub_rn(ray.oy, py))), inv);
+    gz = __fdiv_rn(__fmaf_rn(num, ray.dz, __fmul_rn(dp, __fsub_rn(ray.oz, pz))), inv);
 }
+
+// Per-ray state of the backward pass and the analytic gradients of one composited cell
+// (backward cell functor, pipeline.cu:219-331; SURVEY.md Appendix A.4/A.5, quirks kept).
+// Shared by both backward kernels; every multiply-add is pinned to the reference's SASS
+// association for the reason given at isect_grad().
+struct BackwardRay {
+    float out[4];   // saved forward rgba
+    float g[4];     // dL/drgba
+    float k_alpha;  // (1 - rgba.a) * dL/da, constant per ray
+    float err;
+    uint32_t Q, qi;
+    const float *qv, *dg;
+    float cq, cdg;
+    float T, cr, cg, cb;
+    uint32_t prev;
+    float ppx, ppy, ppz; // prev_point (zero before the first composited cell: quirk A.5.2)
+    float pgx, pgy, pgz; // prev_point_grad
+    float cgx, cgy, cgz; // current_point_grad
+
+    __device__ __forceinline__ void init() {
+        T = 1.0f;
+        cr = cg = cb = 0.0f;
+        prev = kNone;
+        ppx = ppy = ppz = 0.0f;
+        pgx = pgy = pgz = 0.0f;
+        cgx = cgy = cgz = 0.0f;
+        qi = 0;
+        cdg = 0.0f;
+        k_alpha = __fmul_rn(__fsub_rn(1.0f, out[3]), g[3]);
+    }
+
+    // Gradients of one cell.  Outputs: dL/drgb (ReLU-masked), dL/dsigma, and -- when
+    // `flush` -- the finished position gradient (fx,fy,fz) of point `flush_idx` (the
+    // previous composited cell: gradients are flushed one cell late, quirk A.5.1).
+    // Returns whether the ray continues.
+    __device__ __forceinline__ bool cell(uint32_t cur, const float4 &pc, const float4 &pn,
+                                         float t0, float t1, const float rgb[3],
+                                         const RayGeom &ray, float weight_threshold,
+                                         float dL_drgb[3], float &dL_ds, float &w_out, bool &flush,
+                                         uint32_t &flush_idx, float &fx_, float &fy_, float &fz_) {
+        const float s = pc.w;
+        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+        float alpha = 1.0f - expf(__fmul_rn(s, -delta));
+        float oma = __fsub_rn(1.0f, alpha);
+        float omae = __fadd_rn(oma, 1e-6f);
+        float denom = __fmul_rn(omae, T);
+        float w = __fmul_rn(alpha, T);
+        w_out = w;
+        cr = __fmaf_rn(w, rgb[0], cr);
+        cg = __fmaf_rn(w, rgb[1], cg);
+        cb = __fmaf_rn(w, rgb[2], cb);
+        float rest0 = __fdiv_rn(__fsub_rn(out[0], cr), denom);
+        float rest1 = __fdiv_rn(__fsub_rn(out[1], cg), denom);
+        float rest2 = __fdiv_rn(__fsub_rn(out[2], cb), denom);
+        float dot = __fmaf_rn(g[0], __fsub_rn(rgb[0], rest0),
+                              __fmaf_rn(g[1], __fsub_rn(rgb[1], rest1),
+                                        __fmul_rn(g[2], __fsub_rn(rgb[2], rest2))));
+        float dL_dalpha = __fmaf_rn(dot, T, __fdiv_rn(k_alpha, omae));
+        float Tn = __fmul_rn(oma, T);
+        dL_ds = __fmul_rn(dL_dalpha, __fmul_rn(delta, oma));
+        float dL_dt0 = 0.0f;
+        while (qi < Q && Tn < cq) {
+            float gq = __fdiv_rn(__ldg(dg + qi), s);
+            dL_dt0 = __fadd_rn(gq, dL_dt0);
+            float m = __fmul_rn(logf(__fdiv_rn(T, cq)), gq);
+            dL_ds = __fsub_rn(dL_ds, __fdiv_rn(m, s));
+            cdg = __fsub_rn(cdg, gq);
+            qi++;
+            if (qi < Q)
+                cq = __ldg(qv + qi);
+        }
+        float dL_dd = __fmul_rn(dL_dalpha, (delta > 0.0f) ? __fmul_rn(s, oma) : 0.0f);
+        if (qi < Q) {
+            dL_ds = __fmaf_rn(cdg, -delta, dL_ds);
+            dL_dd = __fmaf_rn(cdg, -s, dL_dd);
+        }
+        dL_dt0 = __fsub_rn(dL_dt0, dL_dd);
+        const float dL_dt1 = dL_dd;
+
+        // position gradients through t0 / t1 (pipeline.cu:284-313)
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        if (prev != kNone)
+            isect_grad(ppx, ppy, ppz, pc.x, pc.y, pc.z, ray, ax, ay, az); // dt0/dprev
+        float bx, by, bz, ex, ey, ez, nx, ny, nz;
+        isect_grad(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz); // dt1/dcur
+        isect_grad(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez);    // dt0/dcur
+        isect_grad(pn.x, pn.y, pn.z, pc.x, pc.y, pc.z, ray, nx, ny, nz); // dt1/dnext
+        pgx = __fmaf_rn(dL_dt0, ax, pgx);
+        pgy = __fmaf_rn(dL_dt0, ay, pgy);
+        pgz = __fmaf_rn(dL_dt0, az, pgz);
+        cgx = __fadd_rn(cgx, __fmaf_rn(dL_dt0, ex, __fmul_rn(dL_dt1, bx)));
+        cgy = __fadd_rn(cgy, __fmaf_rn(dL_dt0, ey, __fmul_rn(dL_dt1, by)));
+        cgz = __fadd_rn(cgz, __fmaf_rn(dL_dt0, ez, __fmul_rn(dL_dt1, bz)));
+        flush = prev != kNone;
+        flush_idx = prev;
+        fx_ = pgx; fy_ = pgy; fz_ = pgz;
+        ppx = pc.x; ppy = pc.y; ppz = pc.z;
+        prev = cur;
+        pgx = cgx; pgy = cgy; pgz = cgz;
+        cgx = __fmul_rn(dL_dt1, nx);
+        cgy = __fmul_rn(dL_dt1, ny);
+        cgz = __fmul_rn(dL_dt1, nz);
+
+        T = Tn;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = __fmul_rn(g[c], w);
+            dL_drgb[c] = (rgb[c] == 0.0f) ? 0.0f : v;
+        }
+        return T > weight_threshold;
+    }
+};
 
 // ray index of this thread.  image_width == 0: linear.  Otherwise the rays are a
 // row-major image; a CTA of 128 threads covers a 16x8 pixel block and each warp

@@ -212,6 +212,77 @@ struct BackwardParams {
     int io_half;
 };
 
+// Loads this thread's ray and upstream gradients (pipeline.cu:156-207).
+template <int DEG>
+__device__ __forceinline__ void backward_ray_setup(const BackwardParams &p, uint32_t r, RayGeom &ray,
+                                                   float *sh, BackwardRay &st) {
+    const float *rp = p.rays + 6 * (uint64_t)r;
+    ray.ox = __ldg(rp + 0);
+    ray.oy = __ldg(rp + 1);
+    ray.oz = __ldg(rp + 2);
+    ray.dx = __ldg(rp + 3);
+    ray.dy = __ldg(rp + 4);
+    ray.dz = __ldg(rp + 5);
+    normalize_dir(ray.dx, ray.dy, ray.dz);
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+    st.err = 0.0f;
+    if (p.io_half) {
+        const __half *o = reinterpret_cast<const __half *>(p.rgba) + 4 * (uint64_t)r;
+        const __half *gg = reinterpret_cast<const __half *>(p.rgba_grad) + 4 * (uint64_t)r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            st.out[c] = __half2float(o[c]);
+            st.g[c] = __half2float(gg[c]);
+        }
+        if (p.ray_error)
+            st.err = __half2float(reinterpret_cast<const __half *>(p.ray_error)[r]);
+    } else {
+        float4 o = __ldg(reinterpret_cast<const float4 *>(p.rgba) + r);
+        float4 gg = __ldg(reinterpret_cast<const float4 *>(p.rgba_grad) + r);
+        st.out[0] = o.x; st.out[1] = o.y; st.out[2] = o.z; st.out[3] = o.w;
+        st.g[0] = gg.x; st.g[1] = gg.y; st.g[2] = gg.z; st.g[3] = gg.w;
+        if (p.ray_error)
+            st.err = __ldg(reinterpret_cast<const float *>(p.ray_error) + r);
+    }
+    st.init();
+    st.Q = p.quantiles ? p.num_q : 0u;
+    st.qv = p.quantiles + (uint64_t)r * p.num_q;
+    st.dg = p.depth_grad + (uint64_t)r * p.num_q;
+    st.cq = st.Q ? __ldg(st.qv) : 0.0f;
+    for (uint32_t i = 0; i < st.Q; ++i) { // pipeline.cu:196-207
+        uint32_t pi = __ldg(p.qidx + (uint64_t)r * st.Q + i);
+        if (pi != kNone)
+            st.cdg = __fadd_rn(st.cdg, __fdiv_rn(__ldg(st.dg + i), ldg4(p.cells + pi).w));
+    }
+}
+
+__device__ __forceinline__ void add_point_error(const BackwardParams &p, uint32_t cell, float v) {
+    if (p.io_half)
+        atomicAdd(reinterpret_cast<__half *>(p.point_error) + cell, __float2half_rn(v));
+    else
+        atomicAdd(reinterpret_cast<float *>(p.point_error) + cell, v);
+}
+
+// one gradient row as 128-bit reductions (write_rgb_grad_to_sh, sh_utils.cuh:85-92, plus the
+// density slot); a row whose three channel gradients are all zero adds nothing and is skipped
+template <int DEG>
+__device__ __forceinline__ void reduce_row_direct(float *row, const float *sh, const float dL_drgb[3],
+                                                  float dL_ds) {
+    constexpr int SR = sh_row(DEG);
+    if (dL_drgb[0] != 0.0f || dL_drgb[1] != 0.0f || dL_drgb[2] != 0.0f) {
+#pragma unroll
+        for (int i = 0; i < SR; i += 4) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                v[k] = (i + k < 3 * sh_dim(DEG)) ? __fmul_rn(sh[(i + k) / 3], dL_drgb[(i + k) % 3]) : 0.0f;
+            red_add_v4(row + i, v[0], v[1], v[2], v[3]);
+        }
+    }
+    red_add_v4(row + SR, dL_ds, 0.0f, 0.0f, 0.0f);
+}
+
+// ---- backward, direct: every lane reduces its own rows straight to HBM
 template <int DEG, typename Faces>
 __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p, const Faces fa) {
     uint32_t r;
@@ -219,165 +290,44 @@ __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p
         return;
     constexpr int GR = grad_row(DEG);
     constexpr int SR = sh_row(DEG);
-
     RayGeom ray;
-    {
-        const float *rp = p.rays + 6 * (uint64_t)r;
-        ray.ox = __ldg(rp + 0);
-        ray.oy = __ldg(rp + 1);
-        ray.oz = __ldg(rp + 2);
-        ray.dx = __ldg(rp + 3);
-        ray.dy = __ldg(rp + 4);
-        ray.dz = __ldg(rp + 5);
-        normalize_dir(ray.dx, ray.dy, ray.dz);
-    }
     float sh[sh_dim(DEG)];
-    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
-
-    float out[4], g[4], err = 0.0f;
-    if (p.io_half) {
-        const __half *o = reinterpret_cast<const __half *>(p.rgba) + 4 * (uint64_t)r;
-        const __half *gg = reinterpret_cast<const __half *>(p.rgba_grad) + 4 * (uint64_t)r;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            out[c] = __half2float(o[c]);
-            g[c] = __half2float(gg[c]);
-        }
-        if (p.ray_error)
-            err = __half2float(reinterpret_cast<const __half *>(p.ray_error)[r]);
-    } else {
-        float4 o = __ldg(reinterpret_cast<const float4 *>(p.rgba) + r);
-        float4 gg = __ldg(reinterpret_cast<const float4 *>(p.rgba_grad) + r);
-        out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
-        g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
-        if (p.ray_error)
-            err = __ldg(reinterpret_cast<const float *>(p.ray_error) + r);
-    }
-
-    const uint32_t Q = p.quantiles ? p.num_q : 0u;
-    const float *qv = p.quantiles + (uint64_t)r * p.num_q;
-    const float *dg = p.depth_grad + (uint64_t)r * p.num_q;
-    uint32_t qi = 0;
-    float cq = Q ? __ldg(qv) : 0.0f;
-    float cdg = 0.0f; // pipeline.cu:196-207
-    for (uint32_t i = 0; i < Q; ++i) {
-        uint32_t pi = __ldg(p.qidx + (uint64_t)r * Q + i);
-        if (pi != kNone)
-            cdg += __ldg(dg + i) / ldg4(p.cells + pi).w;
-    }
-
-    float T = 1.0f;
-    float cr = 0.0f, cg = 0.0f, cb = 0.0f;
-    uint32_t prev = kNone;
-    float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;    // prev_point
-    float pgx = 0.0f, pgy = 0.0f, pgz = 0.0f;    // prev_point_grad
-    float cgx = 0.0f, cgy = 0.0f, cgz = 0.0f;    // current_point_grad
+    BackwardRay st;
+    backward_ray_setup<DEG>(p, r, ray, sh, st);
 
     auto cell_fn = [&](uint32_t cell, const float4 &pc, float t0, float t1, const float4 &pn) -> bool {
-        float s = pc.w;
         float rgb[3] = {0.0f, 0.0f, 0.0f};
-        if (s > 1e-6f)
+        if (pc.w > 1e-6f)
             sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cell * SR, sh, rgb[0], rgb[1], rgb[2]);
-        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
-        float alpha = 1.0f - expf(-s * delta);
-        float w = __fmul_rn(T, alpha);
-        float one_m_alpha = __fsub_rn(1.0f, alpha);
-        float dalpha_ds = delta * one_m_alpha;
-        float dalpha_dd = (delta > 0.0f) ? s * one_m_alpha : 0.0f;
-        cr = __fmaf_rn(w, rgb[0], cr);
-        cg = __fmaf_rn(w, rgb[1], cg);
-        cb = __fmaf_rn(w, rgb[2], cb);
-        if (p.point_error) {
-            if (p.io_half)
-                atomicAdd(reinterpret_cast<__half *>(p.point_error) + cell, __float2half_rn(w * err));
-            else
-                atomicAdd(reinterpret_cast<float *>(p.point_error) + cell, w * err);
-        }
-        float dL_drgb[3] = {g[0] * w, g[1] * w, g[2] * w};
-        float denom = T * (one_m_alpha + 1e-6f);
-        float rest0 = (out[0] - cr) / denom, rest1 = (out[1] - cg) / denom, rest2 = (out[2] - cb) / denom;
-        float dL_dalpha = T * ((rgb[0] - rest0) * g[0] + ((rgb[1] - rest1) * g[1] + (rgb[2] - rest2) * g[2]));
-        dL_dalpha += (1.0f - out[3]) * g[3] / (one_m_alpha + 1e-6f);
-        float dL_ds = dL_dalpha * dalpha_ds;
-        float dL_dd = dL_dalpha * dalpha_dd;
-        float dL_dt0 = 0.0f;
-
-        float Tn = __fmul_rn(T, one_m_alpha);
-        while (qi < Q && Tn < cq) {
-            float gq = __ldg(dg + qi) / s;
-            dL_dt0 += gq;
-            dL_ds += -gq * logf(__fdiv_rn(T, cq)) / s;
-            cdg -= gq;
-            qi++;
-            if (qi < Q)
-                cq = __ldg(qv + qi);
-        }
-        if (qi < Q) {
-            dL_ds += -delta * cdg;
-            dL_dd += -s * cdg;
-        }
-        dL_dt0 += -dL_dd;
-        float dL_dt1 = dL_dd;
-
-        // position gradients through t0 / t1 (pipeline.cu:284-313, quirks A.5.1-3 kept)
-        float ax = 0.0f, ay = 0.0f, az = 0.0f;
-        if (prev != kNone)
-            isect_grad(ppx, ppy, ppz, pc.x, pc.y, pc.z, ray, ax, ay, az); // dt0/dprev
-        float bx, by, bz, ex, ey, ez, fx, fy, fz;
-        isect_grad(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz);   // dt1/dcur
-        isect_grad(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez);      // dt0/dcur
-        isect_grad(pn.x, pn.y, pn.z, pc.x, pc.y, pc.z, ray, fx, fy, fz);   // dt1/dnext
-        pgx += dL_dt0 * ax; pgy += dL_dt0 * ay; pgz += dL_dt0 * az;
-        cgx += dL_dt0 * ex + dL_dt1 * bx;
-        cgy += dL_dt0 * ey + dL_dt1 * by;
-        cgz += dL_dt0 * ez + dL_dt1 * bz;
-        if (prev != kNone)
-            red_add_v4(p.acc + (uint64_t)prev * GR + SR, 0.0f, pgx, pgy, pgz);
-        ppx = pc.x; ppy = pc.y; ppz = pc.z;
-        prev = cell;
-        pgx = cgx; pgy = cgy; pgz = cgz;
-        cgx = dL_dt1 * fx; cgy = dL_dt1 * fy; cgz = dL_dt1 * fz;
-
-        T = Tn;
-
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            if (rgb[c] == 0.0f)
-                dL_drgb[c] = 0.0f;
-        float *row = p.acc + (uint64_t)cell * GR;
-        // write_rgb_grad_to_sh (sh_utils.cuh:85-92) as 128-bit reductions; a row whose
-        // three channel gradients are all zero adds nothing and is skipped.
-        if (dL_drgb[0] != 0.0f || dL_drgb[1] != 0.0f || dL_drgb[2] != 0.0f) {
-            float v[SR];
-#pragma unroll
-            for (int i = 0; i < SR; ++i)
-                v[i] = (i < 3 * sh_dim(DEG)) ? sh[i / 3] * dL_drgb[i % 3] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < SR; i += 4)
-                red_add_v4(row + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        red_add_v4(row + SR, dL_ds, 0.0f, 0.0f, 0.0f);
-        return T > p.weight_threshold;
+        float dL_drgb[3], dL_ds, w, fx, fy, fz;
+        bool flush;
+        uint32_t flush_idx;
+        bool go = st.cell(cell, pc, pn, t0, t1, rgb, ray, p.weight_threshold, dL_drgb, dL_ds, w, flush,
+                          flush_idx, fx, fy, fz);
+        if (p.point_error)
+            add_point_error(p, cell, __fmul_rn(w, st.err));
+        if (flush)
+            red_add_v4(p.acc + (uint64_t)flush_idx * GR + SR, 0.0f, fx, fy, fz);
+        reduce_row_direct<DEG>(p.acc + (uint64_t)cell * GR, sh, dL_drgb, dL_ds);
+        return go;
     };
-
     walk(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn);
 }
 
-// ------------------------------------------------------------------ backward, warp-aggregated
-// Same mathematics as backward_kernel; what changes is how the per-cell gradient rows reach
-// HBM.  Neighbouring rays of an 8x4 tile cross mostly the same cells, a few iterations apart
-// (one ray clips a sliver cell the other misses and they drift out of lock-step), so instead of
-// 13 x 128-bit reductions per lane per step the warp keeps a small direct-mapped cache of
-// gradient rows in shared memory:
-//   * every lane with a contribution writes its row (SH products + density grad) to a staging
-//     row in shared memory;
-//   * lanes are grouped by cell (MATCH.ANY); for each group the warp sums the staged rows
-//     "transposed" -- lane j owns elements 2j, 2j+1 of the row -- so the shared-memory update
-//     needs no atomics and has no bank conflicts, and adds the sum to the cell's cache row;
+// ---- backward, warp-aggregated
+// Same mathematics; what changes is how the per-cell gradient rows reach HBM.  Neighbouring
+// rays of an 8x4 tile cross mostly the same cells, a few iterations apart (one ray clips a
+// sliver cell the other misses and they drift out of lock-step), so instead of 13 x 128-bit
+// reductions per lane per step the warp keeps a small direct-mapped cache of gradient rows in
+// shared memory:
+//   * lanes are grouped by cell (MATCH.ANY); a lane that is alone in its cell issues its
+//     reductions directly, in parallel with the other singleton lanes;
+//   * every lane of a multi-lane group writes its row (SH products + density grad) to a
+//     staging row in shared memory; the warp sums the staged rows of a group "transposed" --
+//     lane j owns elements 2j, 2j+1 of the row -- so the shared-memory update needs no atomics
+//     and has no bank conflicts, and adds the sum to the cell's cache row;
 //   * a cache row is written to HBM (13 lanes x one RED.128) only when its slot is claimed by
-//     another cell, or at the end of the warp's rays;
-//   * a lane that is alone in its cell skips all of that and issues its reductions directly,
-//     in parallel with the other singleton lanes.
+//     another cell, or when the warp's rays are finished.
 // Position gradients (3 floats to the previous composited cell) stay direct reductions.
 template <int DEG, typename Faces, int SLOTS>
 __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardParams p, const Faces fa) {
@@ -391,8 +341,8 @@ __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardP
     extern __shared__ __align__(16) float smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARP_FLOATS = 32 * GR + SLOTS * GR + SLOTS;
-    float *stage = smem + warp * WARP_FLOATS;       // [32][GR]
-    float *cache = stage + 32 * GR;                 // [SLOTS][GR]
+    float *stage = smem + warp * WARP_FLOATS;                          // [32][GR]
+    float *cache = stage + 32 * GR;                                    // [SLOTS][GR]
     uint32_t *tags = reinterpret_cast<uint32_t *>(cache + SLOTS * GR); // [SLOTS]
     for (int i = lane; i < SLOTS; i += 32)
         tags[i] = kNone;
@@ -400,67 +350,25 @@ __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardP
 
     uint32_t r;
     bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
-
     RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
     float sh[sh_dim(DEG)];
-    float out[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, err = 0.0f;
-    uint32_t Q = 0, qi = 0;
-    const float *qv = nullptr, *dg = nullptr;
-    float cq = 0.0f, cdg = 0.0f;
+    BackwardRay st;
     uint32_t cur = 0;
     float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!done) {
-        const float *rp = p.rays + 6 * (uint64_t)r;
-        ray.ox = __ldg(rp + 0);
-        ray.oy = __ldg(rp + 1);
-        ray.oz = __ldg(rp + 2);
-        ray.dx = __ldg(rp + 3);
-        ray.dy = __ldg(rp + 4);
-        ray.dz = __ldg(rp + 5);
-        normalize_dir(ray.dx, ray.dy, ray.dz);
-        if (p.io_half) {
-            const __half *o = reinterpret_cast<const __half *>(p.rgba) + 4 * (uint64_t)r;
-            const __half *gg = reinterpret_cast<const __half *>(p.rgba_grad) + 4 * (uint64_t)r;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                out[c] = __half2float(o[c]);
-                g[c] = __half2float(gg[c]);
-            }
-            if (p.ray_error)
-                err = __half2float(reinterpret_cast<const __half *>(p.ray_error)[r]);
-        } else {
-            float4 o = __ldg(reinterpret_cast<const float4 *>(p.rgba) + r);
-            float4 gg = __ldg(reinterpret_cast<const float4 *>(p.rgba_grad) + r);
-            out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
-            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
-            if (p.ray_error)
-                err = __ldg(reinterpret_cast<const float *>(p.ray_error) + r);
-        }
-        Q = p.quantiles ? p.num_q : 0u;
-        qv = p.quantiles + (uint64_t)r * p.num_q;
-        dg = p.depth_grad + (uint64_t)r * p.num_q;
-        cq = Q ? __ldg(qv) : 0.0f;
-        for (uint32_t i = 0; i < Q; ++i) {
-            uint32_t pi = __ldg(p.qidx + (uint64_t)r * Q + i);
-            if (pi != kNone)
-                cdg += __ldg(dg + i) / ldg4(p.cells + pi).w;
-        }
+        backward_ray_setup<DEG>(p, r, ray, sh, st);
         cur = __ldg(p.start + r);
         pc = ldg4(p.cells + cur);
+    } else {
+#pragma unroll
+        for (int i = 0; i < sh_dim(DEG); ++i)
+            sh[i] = 0.0f;
     }
-    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
-
-    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
-    uint32_t prev = kNone;
-    float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;
-    float pgx = 0.0f, pgy = 0.0f, pgz = 0.0f;
-    float cgx = 0.0f, cgy = 0.0f, cgz = 0.0f;
     float t0 = 0.0f;
     uint32_t n = 0;
 
     for (;;) {
-        bool c_valid = false;   // this lane has a (SH, density) row for cell c_cell this iteration
-        bool c_sh = false;      // ... with a nonzero SH part
+        bool c_valid = false; // this lane has a (SH, density) row for cell c_cell this iteration
         uint32_t c_cell = kNone;
         float dL_ds = 0.0f;
         float dL_drgb[3] = {0.0f, 0.0f, 0.0f};
@@ -481,76 +389,21 @@ __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardP
                     uint32_t nxt = fa.neighbour(begin, face);
                     float4 pn = ldg4(p.cells + nxt);
                     if (t1 > t0) {
-                        float s = pc.w;
                         float rgb[3] = {0.0f, 0.0f, 0.0f};
-                        if (s > 1e-6f)
+                        if (pc.w > 1e-6f)
                             sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * SR, sh, rgb[0], rgb[1], rgb[2]);
-                        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
-                        float alpha = 1.0f - expf(-s * delta);
-                        float w = __fmul_rn(T, alpha);
-                        float one_m_alpha = __fsub_rn(1.0f, alpha);
-                        float dalpha_ds = delta * one_m_alpha;
-                        float dalpha_dd = (delta > 0.0f) ? s * one_m_alpha : 0.0f;
-                        cr = __fmaf_rn(w, rgb[0], cr);
-                        cg = __fmaf_rn(w, rgb[1], cg);
-                        cb = __fmaf_rn(w, rgb[2], cb);
-                        if (p.point_error) {
-                            if (p.io_half)
-                                atomicAdd(reinterpret_cast<__half *>(p.point_error) + cur, __float2half_rn(w * err));
-                            else
-                                atomicAdd(reinterpret_cast<float *>(p.point_error) + cur, w * err);
-                        }
-                        dL_drgb[0] = g[0] * w; dL_drgb[1] = g[1] * w; dL_drgb[2] = g[2] * w;
-                        float denom = T * (one_m_alpha + 1e-6f);
-                        float rest0 = (out[0] - cr) / denom, rest1 = (out[1] - cg) / denom, rest2 = (out[2] - cb) / denom;
-                        float dL_dalpha = T * ((rgb[0] - rest0) * g[0] + ((rgb[1] - rest1) * g[1] + (rgb[2] - rest2) * g[2]));
-                        dL_dalpha += (1.0f - out[3]) * g[3] / (one_m_alpha + 1e-6f);
-                        dL_ds = dL_dalpha * dalpha_ds;
-                        float dL_dd = dL_dalpha * dalpha_dd;
-                        float dL_dt0 = 0.0f;
-                        float Tn = __fmul_rn(T, one_m_alpha);
-                        while (qi < Q && Tn < cq) {
-                            float gq = __ldg(dg + qi) / s;
-                            dL_dt0 += gq;
-                            dL_ds += -gq * logf(__fdiv_rn(T, cq)) / s;
-                            cdg -= gq;
-                            qi++;
-                            if (qi < Q)
-                                cq = __ldg(qv + qi);
-                        }
-                        if (qi < Q) {
-                            dL_ds += -delta * cdg;
-                            dL_dd += -s * cdg;
-                        }
-                        dL_dt0 += -dL_dd;
-                        float dL_dt1 = dL_dd;
-                        float ax = 0.0f, ay = 0.0f, az = 0.0f;
-                        if (prev != kNone)
-                            isect_grad(ppx, ppy, ppz, pc.x, pc.y, pc.z, ray, ax, ay, az);
-                        float bx, by, bz, ex, ey, ez, fx, fy, fz;
-                        isect_grad(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz);
-                        isect_grad(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez);
-                        isect_grad(pn.x, pn.y, pn.z, pc.x, pc.y, pc.z, ray, fx, fy, fz);
-                        pgx += dL_dt0 * ax; pgy += dL_dt0 * ay; pgz += dL_dt0 * az;
-                        cgx += dL_dt0 * ex + dL_dt1 * bx;
-                        cgy += dL_dt0 * ey + dL_dt1 * by;
-                        cgz += dL_dt0 * ez + dL_dt1 * bz;
-                        if (prev != kNone)
-                            red_add_v4(p.acc + (uint64_t)prev * GR + SR, 0.0f, pgx, pgy, pgz);
-                        ppx = pc.x; ppy = pc.y; ppz = pc.z;
-                        prev = cur;
-                        pgx = cgx; pgy = cgy; pgz = cgz;
-                        cgx = dL_dt1 * fx; cgy = dL_dt1 * fy; cgz = dL_dt1 * fz;
-                        T = Tn;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            if (rgb[c] == 0.0f)
-                                dL_drgb[c] = 0.0f;
+                        float w, fx, fy, fz;
+                        bool flush;
+                        uint32_t flush_idx;
+                        bool go = st.cell(cur, pc, pn, t0, t1, rgb, ray, p.weight_threshold, dL_drgb, dL_ds,
+                                          w, flush, flush_idx, fx, fy, fz);
+                        if (p.point_error)
+                            add_point_error(p, cur, __fmul_rn(w, st.err));
+                        if (flush)
+                            red_add_v4(p.acc + (uint64_t)flush_idx * GR + SR, 0.0f, fx, fy, fz);
                         c_valid = true;
                         c_cell = cur;
-                        c_sh = dL_drgb[0] != 0.0f || dL_drgb[1] != 0.0f || dL_drgb[2] != 0.0f;
-                        if (!(T > p.weight_threshold))
-                            done = true;
+                        done = !go;
                     }
                     t0 = fmaxf(t0, t1);
                     cur = nxt;
@@ -563,20 +416,8 @@ __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardP
         unsigned grp = __match_any_sync(FULL, c_valid ? c_cell : (0x80000000u | lane));
         bool single = c_valid && (grp & (grp - 1)) == 0;
         bool staged = c_valid && !single;
-        if (single) {
-            float *row = p.acc + (uint64_t)c_cell * GR;
-            if (c_sh) {
-#pragma unroll
-                for (int i = 0; i < SR; i += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        v[k] = (i + k < 3 * sh_dim(DEG)) ? sh[(i + k) / 3] * dL_drgb[(i + k) % 3] : 0.0f;
-                    red_add_v4(row + i, v[0], v[1], v[2], v[3]);
-                }
-            }
-            red_add_v4(row + SR, dL_ds, 0.0f, 0.0f, 0.0f);
-        }
+        if (single)
+            reduce_row_direct<DEG>(p.acc + (uint64_t)c_cell * GR, sh, dL_drgb, dL_ds);
         unsigned todo = __ballot_sync(FULL, staged);
         if (todo) {
             if (staged) {
@@ -586,7 +427,7 @@ __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardP
                     float v[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        v[k] = (i + k < 3 * sh_dim(DEG)) ? sh[(i + k) / 3] * dL_drgb[(i + k) % 3] : 0.0f;
+                        v[k] = (i + k < 3 * sh_dim(DEG)) ? __fmul_rn(sh[(i + k) / 3], dL_drgb[(i + k) % 3]) : 0.0f;
                     srow[i / 4] = make_float4(v[0], v[1], v[2], v[3]);
                 }
                 srow[SR / 4] = make_float4(dL_ds, 0.0f, 0.0f, 0.0f);

@@ -185,8 +185,15 @@ def test_prefetch_adjacent_diff_bit_exact(torch_cuda):
 
 
 # ------------------------------------------------------------------ vs the reference's own kernels
+@pytest.fixture(params=["cached", "direct"])
+def bwd_mode(request, monkeypatch):
+    """Both backward kernels (warp-aggregated shared-memory cache / direct reductions)."""
+    monkeypatch.setenv("RFB_BWD_MODE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
-def test_config1_matches_reference_kernels(torch_cuda, deg):
+def test_config1_matches_reference_kernels(torch_cuda, deg, bwd_mode):
     case = common.config1(deg, 2)
     got = run_ours(torch_cuda, case, return_contribution=True)
     ref = run_ref_gpu(torch_cuda, case, return_contribution=True)
@@ -196,7 +203,7 @@ def test_config1_matches_reference_kernels(torch_cuda, deg):
 
 
 @pytest.mark.parametrize("inside", [False, True])
-def test_scene_matches_reference_kernels(torch_cuda, inside):
+def test_scene_matches_reference_kernels(torch_cuda, inside, bwd_mode):
     case = common.scene_case(num_points=60000, width=320, height=200, inside=inside)
     got = run_ours(torch_cuda, case)
     ref = run_ref_gpu(torch_cuda, case)
@@ -209,7 +216,7 @@ def test_scene_matches_reference_kernels(torch_cuda, inside):
     assert ours <= max(GRAD_TOL, 4 * noise)
 
 
-def test_random_ray_batch_matches_reference_kernels(torch_cuda):
+def test_random_ray_batch_matches_reference_kernels(torch_cuda, bwd_mode):
     case = common.random_ray_case(num_points=60000, num_rays=100000)
     got, ref = run_ours(torch_cuda, case), run_ref_gpu(torch_cuda, case)
     assert_forward_equal(got, ref)
