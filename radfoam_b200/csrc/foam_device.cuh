@@ -237,6 +237,31 @@ struct PaddedFaces {
                 best = fminf(best, q);
             }
         }
+        if (best == kInf) {
+            // nothing ranked: normally the ray is leaving through an unbounded hull cell (no
+            // face with dp > 0 -> the reference finds no face either).  A cheap dp-only pass
+            // confirms that; only a front face whose quotient overflowed needs the exact scan.
+            bool any_front = false;
+            for (uint32_t f = 0; f < nf; f += 4) {
+                uint4 a = ldg4(p + (f >> 1));
+                uint4 b = ldg4(p + (f >> 1) + 1);
+                uint2 rec[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y),
+                                make_uint2(b.z, b.w)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
+                    __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
+                    float dp = __fmaf_rn(__low2float(hxy), ray.dx,
+                                         __fmaf_rn(__high2float(hxy), ray.dy,
+                                                   __fmul_rn(__low2float(hzw), ray.dz)));
+                    any_front |= dp > 0.0f;
+                }
+            }
+            if (!any_front)
+                return; // face stays kNone, t1 stays +inf
+            scan_exact(begin, nf, px, py, pz, ray, t1, face);
+            return;
+        }
         // 2^-19 relative clearance; |second| is capped at 4|best| because beyond that the gap
         // itself dwarfs any rounding (and so that a lone candidate, second == +inf, is clear)
         float ab = fabsf(best);

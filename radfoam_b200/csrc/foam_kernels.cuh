@@ -329,8 +329,12 @@ __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p
 //   * a cache row is written to HBM (13 lanes x one RED.128) only when its slot is claimed by
 //     another cell, or when the warp's rays are finished.
 // Position gradients (3 floats to the previous composited cell) stay direct reductions.
-template <int DEG, typename Faces, int SLOTS>
-__global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardParams p, const Faces fa) {
+// MIN_GROUP: smallest same-cell lane group routed through the cache (smaller groups reduce
+// directly: all such lanes issue their 13 reductions simultaneously, which costs fewer issue
+// slots than one serial cache round per group, at the price of more L2 atomic traffic).
+template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+    backward_cached_kernel(const BackwardParams p, const Faces fa) {
     constexpr int GR = grad_row(DEG);
     constexpr int SR = sh_row(DEG);
     constexpr int HALF_ROW = GR / 2; // lanes that own two row elements each
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(kBlock) backward_cached_kernel(const BackwardP
 
         // ---- warp-collective phase: route this iteration's rows
         unsigned grp = __match_any_sync(FULL, c_valid ? c_cell : (0x80000000u | lane));
-        bool single = c_valid && (grp & (grp - 1)) == 0;
+        bool single = c_valid && __popc(grp) < MIN_GROUP;
         bool staged = c_valid && !single;
         if (single)
             reduce_row_direct<DEG>(p.acc + (uint64_t)c_cell * GR, sh, dL_drgb, dL_ds);

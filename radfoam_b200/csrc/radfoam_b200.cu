@@ -217,32 +217,48 @@ int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t
     return 0;
 }
 
-constexpr int kCacheSlots = 32;
-
-template <int DEG, typename Faces>
-int launch_backward_cached_deg(const BackwardParams &bp, const Faces &fa, uint32_t blocks,
+template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
+int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, uint32_t blocks,
                                cudaStream_t stream) {
     constexpr int GR = grad_row(DEG);
-    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * GR + kCacheSlots * GR + kCacheSlots) * sizeof(float);
-    static bool configured = false; // per template instantiation; idempotent attribute
+    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * GR + SLOTS * GR + SLOTS) * sizeof(float);
+    auto kernel = backward_cached_kernel<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS>;
+    static bool configured = false; // per instantiation; the attribute is idempotent
     if (!configured) {
-        RFB_CUDA(cudaFuncSetAttribute(backward_cached_kernel<DEG, Faces, kCacheSlots>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    backward_cached_kernel<DEG, Faces, kCacheSlots><<<blocks, kBlock, smem, stream>>>(bp, fa);
+    kernel<<<blocks, kBlock, smem, stream>>>(bp, fa);
     RFB_LAUNCHED();
     return 0;
+}
+
+template <int DEG, typename Faces>
+int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
+                               cudaStream_t stream) {
+    // Shipped configuration: 8 cache slots per warp, groups of >= 8 lanes go through the
+    // cache, 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200):
+    // direct 29.3 ms; (32 slots, >=2, 4 CTAs) 21.5; (16, >=4, 5) 17.7; (16, >=8, 5) 16.6;
+    // (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower (profiles/r01_backward_variants.json).
+    // RFB_BWD_VARIANT selects the neighbours kept for re-tuning on other scenes.
+    switch (variant) {
+    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 12, 5>(bp, fa, blocks, stream);
+    case 2: return launch_backward_cached_cfg<DEG, Faces, 4, 8, 5>(bp, fa, blocks, stream);
+    case 3: return launch_backward_cached_cfg<DEG, Faces, 8, 6, 5>(bp, fa, blocks, stream);
+    default: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, blocks, stream);
+    }
 }
 
 template <typename Faces>
 int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
                            cudaStream_t stream) {
+    const char *v = getenv("RFB_BWD_VARIANT");
+    int variant = v ? atoi(v) : 0;
     switch (deg) {
-    case 0: return launch_backward_cached_deg<0>(bp, fa, blocks, stream);
-    case 1: return launch_backward_cached_deg<1>(bp, fa, blocks, stream);
-    case 2: return launch_backward_cached_deg<2>(bp, fa, blocks, stream);
-    default: return launch_backward_cached_deg<3>(bp, fa, blocks, stream);
+    case 0: return launch_backward_cached_deg<0>(0, bp, fa, blocks, stream);
+    case 1: return launch_backward_cached_deg<1>(0, bp, fa, blocks, stream);
+    case 2: return launch_backward_cached_deg<2>(0, bp, fa, blocks, stream);
+    default: return launch_backward_cached_deg<3>(variant, bp, fa, blocks, stream);
     }
 }
 

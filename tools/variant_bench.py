@@ -1,0 +1,44 @@
+"""Time backward variants (RFB_BWD_MODE / RFB_BWD_VARIANT env switches) on one foam."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+import radfoam_b200  # noqa: E402
+from tools.quick_bench import timeit  # noqa: E402
+
+points = int(sys.argv[1]) if len(sys.argv) > 1 else 1_048_576
+f = bench.load_or_build_foam(points, print)
+frame = bench.make_frame(f, 1920, 1080)
+d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+scene = [d(x) for x in (f.points, f.attributes, f.adjacency, f.offsets)]
+fr = {k: d(v) for k, v in frame.items()}
+pipe = radfoam_b200.create_pipeline(3)
+fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
+res = {"fwd_ms": timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))}
+
+
+def bwd():
+    return pipe.trace_backward(*scene, fr["rays"], fr["start"], fwd["rgba"], fr["grad_rgba"], fr["dq"],
+                               fwd["depth_indices"], fr["grad_depth"])
+
+
+os.environ["RFB_BWD_MODE"] = "direct"
+base = bwd()
+res["direct_ms"] = timeit(bwd)
+os.environ["RFB_BWD_MODE"] = "cached"
+for v in range(4):
+    os.environ["RFB_BWD_VARIANT"] = str(v)
+    out = bwd()
+    err = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
+    res[f"cached_v{v}_ms"] = timeit(bwd)
+    res[f"cached_v{v}_err_vs_direct"] = err
+print(json.dumps(res, indent=1))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/variant_bench.json", "w"), indent=1)
