@@ -225,7 +225,9 @@ def run_ours(args):
     R_total = H * W
 
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-    points, attrs = d(f.points), d(f.attributes)
+    # scene parameters are trainable (requires_grad), as in train.py: this is what makes the
+    # forward record the walk tape for the backward of the same step
+    points, attrs = d(f.points).requires_grad_(True), d(f.attributes).requires_grad_(True)
     adj, off = d(f.adjacency), d(f.offsets)
     pipe = radfoam_b200.create_pipeline(3, "float32")
     tracer = sharded.ShardedTracer(pipe)
@@ -244,22 +246,46 @@ def run_ours(args):
                                     scrub_nonfinite=True)
         return fwd, bwd
 
-    pts_p = points.clone().requires_grad_(True)
-    attrs_p = attrs.clone().requires_grad_(True)
+    pts_p = points.detach().clone().requires_grad_(True)
+    attrs_p = attrs.detach().clone().requires_grad_(True)
 
-    def step_e2e():
-        rays = shard_host["rays"].to(dev, non_blocking=True)
-        start = shard_host["start"].to(dev, non_blocking=True)
-        dq = shard_host["dq"].to(dev, non_blocking=True)
-        target = shard_host["target"].to(dev, non_blocking=True)
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def h2d_async():
+        """Enqueue this step's inputs host -> device on the copy stream (like the reference's
+        BatchFetcher, src/utils/batch_fetcher.cpp:44-117: async H2D on a private stream)."""
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            batch = {k: shard_host[k].to(dev, non_blocking=True) for k in ("rays", "start", "dq", "target")}
+            for t in batch.values():
+                t.record_stream(main)
+            ev = copy_stream.record_event()
+        return batch, ev
+
+    def step_e2e(batch, ev):
+        torch.cuda.current_stream(dev).wait_event(ev)
         pipe.invalidate_cache()
         pts_p.grad = None
         attrs_p.grad = None
-        rgba, depth, _, _ = sharded.ShardedTraceRays.apply(tracer, pts_p, attrs_p, adj, off, rays, start, dq, False)
+        rgba, depth, _, _ = sharded.ShardedTraceRays.apply(tracer, pts_p, attrs_p, adj, off, batch["rays"],
+                                                           batch["start"], batch["dq"], False)
         # train.py:187-204 shape: colour loss + depth-quantile regulariser (sums: shards add up)
-        loss = ((rgba - target) ** 2).sum() / R_total + 1e-4 * (depth[..., 0] - depth[..., 1]).abs().sum() / R_total
+        loss = (((rgba - batch["target"]) ** 2).sum() / R_total
+                + 1e-4 * (depth[..., 0] - depth[..., 1]).abs().sum() / R_total)
         loss.backward()
-        return float(loss.item())  # D2H read of the step's result
+        return loss
+
+    def run_e2e(steps):
+        """K steps; every step's H2D copy is issued inside this region, one step ahead of its use
+        (copy of step i+1 overlaps the kernels of step i); the loss is read back every step."""
+        nxt = h2d_async()
+        last = 0.0
+        for i in range(steps):
+            batch, ev = nxt
+            if i + 1 < steps:
+                nxt = h2d_async()
+            last = float(step_e2e(batch, ev).item())  # D2H read of the step's result
+        return last
 
     # --- warm-up (also gives the work counters)
     for _ in range(max(args.warmup, 3)):
@@ -298,13 +324,11 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
 
     # --- e2e: host buffers -> public autograd op -> loss back on the host
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        loss_val = step_e2e()
+    loss_val = run_e2e(args.steps)
     e1.record()
     barrier(world)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
@@ -329,6 +353,10 @@ def run_ours(args):
             traffic = None
 
     cpu = cpu_baseline(f, frame, log) if not args.no_cpu_baseline else None
+    try:
+        tape = pipe.tape_status()
+    except RuntimeError:
+        tape = None
 
     line = {
         "metric": METRIC, "value": R_total / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s",
@@ -346,6 +374,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "loss": loss_val},
         "gpu_launches": int(launches),
         "kernels_ms": {"forward_kernel": k_fwd, "backward_kernel": k_bwd},
+        "walk_tape": tape,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": dom_bytes,
@@ -358,15 +387,18 @@ def run_ours(args):
 
 def cpu_baseline(f, frame, log):
     """The CPU restatement (oracle/, OpenMP over the host cores) on a bounded sample of the
-    same frame: every 16th 8-row band, sized for ~10-30 s.  Reported baseline, not a target."""
+    same frame (8-row bands spread over it), sized for ~10-30 s.  Reported baseline, not a target."""
     from oracle import oracle
 
     H = frame["rays"].shape[0]
-    rows = np.array([r for r in range(H) if (r // 8) % 16 == 0])
+    # 8-row bands in a bit-reversal-like order (every 16th band first, then the bands between),
+    # so that any prefix of the list is spread over the whole frame
+    bands = sorted(range((H + 7) // 8), key=lambda b: (b % 16, b))
+    rows = np.array([r for b in bands for r in range(8 * b, min(8 * b + 8, H))])
     cores = oracle.max_threads()
 
     def run(rsel):
-        sl = {k: np.ascontiguousarray(v[rsel]) for k, v in frame.items()}
+        sl = {k: np.ascontiguousarray(v[np.sort(rsel)]) for k, v in frame.items()}
         t0 = time.time()
         fwd = oracle.trace_forward(f.points, f.attributes, f.adjacency, f.offsets, sl["rays"], sl["start"],
                                    sl["dq"], num_threads=0)
@@ -375,13 +407,15 @@ def cpu_baseline(f, frame, log):
                               num_threads=0)
         return time.time() - t0, sl["rays"].shape[0] * sl["rays"].shape[1]
 
-    t_probe, n_probe = run(rows[:8])
-    want = min(len(rows), max(8, int(len(rows[:8]) * 15.0 / max(t_probe, 1e-3)) // 8 * 8))
-    t, n = (t_probe, n_probe) if want <= 8 else run(rows[:want])
+    run(rows[:8])                       # spin the thread pool up
+    t_probe, n_probe = run(rows[:64])   # ~6% of the frame
+    want = int(min(len(rows), max(64, 64 * 15.0 / max(t_probe, 1e-3)))) // 8 * 8
+    t, n = (t_probe, n_probe) if want <= 64 else run(rows[:want])
     log(f"cpu_baseline: {n} rays in {t:.1f} s on {cores} threads")
     return {"value": n / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-            "sample": f"{n} rays (8-row bands, every 16th, of the same frame), fwd+bwd, C restatement "
-                      f"with OpenMP, {t:.1f} s"}
+            "sample": f"{n} rays of the same frame ({want} of {H} rows, 8-row bands spread over the frame), "
+                      f"fwd+bwd, C restatement of the path with OpenMP, {t:.1f} s; radfoam itself has no "
+                      f"CPU tracing path"}
 
 
 # ----------------------------------------------------------------------------- reference arm

@@ -96,6 +96,15 @@ typedef struct rfb_launch_opts {
 /* zero non-finite gradient entries in the backward epilogue (what
  * radfoam_model/render.py:98-99 does in two extra passes after the call) */
 #define RFB_FLAG_SCRUB_NONFINITE 1u
+/* trace_forward: also record the walk tape -- (cell, t1) per ray and visited cell, 8 bytes --
+ * so that the backward of the same step can replay it instead of re-scanning faces (the
+ * reference's backward re-walks every ray, pipeline.cu:132-343).  Needs a nonzero scene_version. */
+#define RFB_FLAG_RECORD_TAPE 2u
+/* trace_backward: the caller vouches that rays / start points / quantiles / settings / scene are
+ * those of this pipeline's last recording forward; the library additionally checks pointers,
+ * sizes, settings and scene_version and silently re-walks when anything differs.  Results are
+ * identical either way. */
+#define RFB_FLAG_USE_TAPE 4u
 
 typedef struct rfb_pipeline rfb_pipeline;
 
@@ -184,6 +193,12 @@ void rfb_reset_launch_count(void);
 
 /* drop cached scene mirrors (next call rebuilds) */
 void rfb_invalidate_cache(rfb_pipeline *pipeline);
+
+/* State of the walk tape of the last recording forward (waits for that forward): pool capacity
+ * and chunks requested (8 KB each: 32 steps x 32 rays x 8 bytes), and whether the pool overflowed
+ * (then the backward re-walks and the pool is enlarged for the next recording). */
+int rfb_tape_status(rfb_pipeline *pipeline, uint32_t *capacity_chunks, uint32_t *used_chunks,
+                    uint32_t *overflowed);
 
 /* Live kernel timing for roofline reporting: when enabled, CUDA events are recorded on the
  * launching stream right around the forward / backward ray kernel of every call.

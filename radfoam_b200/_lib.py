@@ -33,6 +33,8 @@ class LaunchOpts(ctypes.Structure):  # rfb_launch_opts
 
 
 FLAG_SCRUB_NONFINITE = 1
+FLAG_RECORD_TAPE = 2
+FLAG_USE_TAPE = 4
 
 # name -> (restype, argtypes); must list every symbol include/radfoam_b200.h declares
 _P = c_void_p
@@ -61,6 +63,7 @@ SIGNATURES = {
     "rfb_launch_count": (c_uint64, []),
     "rfb_reset_launch_count": (None, []),
     "rfb_invalidate_cache": (None, [_P]),
+    "rfb_tape_status": (c_int, [_P, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]),
     "rfb_set_profiling": (None, [_P, c_int]),
     "rfb_last_kernel_ms": (c_int, [_P, c_int, POINTER(c_float)]),
 }

@@ -189,6 +189,160 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ForwardParams p, 
         p.nint[r] = n;
 }
 
+// ------------------------------------------------------------------ the walk tape
+// A training step traces every ray twice: forward, then the backward re-walk
+// (pipeline.cu:132-343 repeats trace<>()).  The face scan is ~2/3 of the walk's instructions,
+// so when a backward pass is expected the forward records, per ray and visited cell,
+// (cell, t1) -- 8 bytes -- and the backward replays that instead of re-scanning faces.  The
+// record stream is identical to what the re-walk would compute (same kernel arithmetic), so
+// results do not change.  Layout: all lanes of a warp are at the same step index k in the same
+// loop iteration, so warp w writes rows of 32 records; rows are grouped in chunks of kTapeChunk
+// steps (8 KB) handed out by a bump allocator, chunk ids in table[w][k / kTapeChunk].  If the
+// pool runs out the overflow flag is raised and the backward re-walks (still correct); the host
+// grows the pool for the next step.
+constexpr int kTapeChunk = 32;     // steps per chunk
+constexpr uint32_t kTapeNoChunk = 0xFFFFFFFFu;
+
+struct Tape {
+    uint2 *pool;        // [capacity][kTapeChunk][32] records (cell, float_as_uint(t1))
+    uint32_t *table;    // [num_warps][table_stride] chunk ids
+    uint2 *per_ray;     // [R] (number of records, cell entered after the last record)
+    uint32_t *ctrl;     // [0] bump cursor, [1] overflow flag
+    uint32_t capacity;  // chunks in the pool
+    uint32_t table_stride;
+};
+
+// Forward with an explicit warp-synchronous loop (all lanes stay in the loop until the warp is
+// done, so lane 0 can allocate tape chunks for the warp) that records the tape.
+template <int DEG, typename Faces>
+__global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
+                                                                const Tape tape) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    uint32_t r;
+    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
+    const bool has_ray = !done;
+
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    float sh[sh_dim(DEG)];
+    uint32_t Q = 0, qi = 0;
+    const float *qv = nullptr;
+    float cq = 0.0f;
+    uint32_t cur = 0;
+    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_ray) {
+        const float *rp = p.rays + 6 * (uint64_t)r;
+        ray.ox = __ldg(rp + 0);
+        ray.oy = __ldg(rp + 1);
+        ray.oz = __ldg(rp + 2);
+        ray.dx = __ldg(rp + 3);
+        ray.dy = __ldg(rp + 4);
+        ray.dz = __ldg(rp + 5);
+        normalize_dir(ray.dx, ray.dy, ray.dz);
+        Q = p.quantiles ? p.num_q : 0u;
+        qv = p.quantiles + (uint64_t)r * p.num_q;
+        cq = Q ? __ldg(qv) : 0.0f;
+        cur = __ldg(p.start + r);
+        pc = ldg4(p.cells + cur);
+    }
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, t0 = 0.0f;
+    uint32_t n = 0, nrec = 0;
+    uint32_t chunk = kTapeNoChunk;
+    for (uint32_t k = 0;; ++k) {
+        if ((k % kTapeChunk) == 0) { // the warp enters a new chunk of steps
+            uint32_t c = kTapeNoChunk;
+            if (lane == 0) {
+                c = atomicAdd(tape.ctrl, 1u);
+                if (c >= tape.capacity || k / kTapeChunk >= tape.table_stride) {
+                    atomicExch(tape.ctrl + 1, 1u);
+                    c = kTapeNoChunk;
+                } else {
+                    tape.table[(uint64_t)gwarp * tape.table_stride + k / kTapeChunk] = c;
+                }
+            }
+            chunk = __shfl_sync(FULL, c, 0);
+        }
+        if (!done) {
+            n++;
+            if (n > p.max_steps) {
+                done = true;
+            } else {
+                uint32_t begin, nf;
+                fa.row(cur, begin, nf);
+                float t1 = __int_as_float(0x7f800000);
+                uint32_t face = kNone;
+                fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                if (face == kNone) {
+                    done = true;
+                } else {
+                    if (chunk != kTapeNoChunk)
+                        tape.pool[((uint64_t)chunk * kTapeChunk + (k % kTapeChunk)) * 32 + lane] =
+                            make_uint2(cur, __float_as_uint(t1));
+                    nrec++;
+                    uint32_t nxt = fa.neighbour(begin, face);
+                    float4 pn = ldg4(p.cells + nxt);
+                    if (t1 > t0) {
+                        float s = pc.w;
+                        float r_ = 0.0f, g_ = 0.0f, b_ = 0.0f;
+                        if (s > 1e-6f)
+                            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * sh_row(DEG), sh, r_, g_, b_);
+                        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+                        float alpha = 1.0f - expf(-s * delta);
+                        float w = __fmul_rn(T, alpha);
+                        if (p.contrib) {
+                            if (p.out_half)
+                                atomicAdd(reinterpret_cast<__half *>(p.contrib) + cur, __float2half_rn(w));
+                            else
+                                atomicAdd(reinterpret_cast<float *>(p.contrib) + cur, w);
+                        }
+                        cr = __fmaf_rn(w, r_, cr);
+                        cg = __fmaf_rn(w, g_, cg);
+                        cb = __fmaf_rn(w, b_, cb);
+                        float Tn = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        while (qi < Q && Tn < cq) {
+                            p.qdepth[(uint64_t)r * Q + qi] = __fadd_rn(t0, __fdiv_rn(logf(__fdiv_rn(T, cq)), s));
+                            p.qidx[(uint64_t)r * Q + qi] = cur;
+                            qi++;
+                            if (qi < Q)
+                                cq = __ldg(qv + qi);
+                        }
+                        T = Tn;
+                        done = !(T > p.weight_threshold);
+                    }
+                    t0 = fmaxf(t0, t1);
+                    cur = nxt;
+                    pc = pn;
+                }
+            }
+        }
+        if (!__any_sync(FULL, !done))
+            break;
+    }
+    if (!has_ray)
+        return;
+    tape.per_ray[r] = make_uint2(nrec, cur);
+    while (qi < Q) {
+        p.qdepth[(uint64_t)r * Q + qi] = -1.0f;
+        p.qidx[(uint64_t)r * Q + qi] = kNone;
+        qi++;
+    }
+    float a = __fsub_rn(1.0f, T);
+    if (p.out_half) {
+        __half2 lo = __floats2half2_rn(cr, cg), hi = __floats2half2_rn(cb, a);
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t *>(&lo);
+        v.y = *reinterpret_cast<uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(p.rgba)[r] = v;
+    } else {
+        reinterpret_cast<float4 *>(p.rgba)[r] = make_float4(cr, cg, cb, a);
+    }
+    if (p.nint)
+        p.nint[r] = n;
+}
+
 // ------------------------------------------------------------------ backward
 struct BackwardParams {
     const float4 *cells;
@@ -332,9 +486,11 @@ __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p
 // MIN_GROUP: smallest same-cell lane group routed through the cache (smaller groups reduce
 // directly: all such lanes issue their 13 reductions simultaneously, which costs fewer issue
 // slots than one serial cache round per group, at the price of more L2 atomic traffic).
+// `tape.pool != nullptr`: replay the forward's record of (cell, t1) instead of re-scanning faces
+// (falls back to the re-walk, uniformly for the whole grid, if the tape overflowed).
 template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
-    backward_cached_kernel(const BackwardParams p, const Faces fa) {
+    backward_cached_kernel(const BackwardParams p, const Faces fa, const Tape tape) {
     constexpr int GR = grad_row(DEG);
     constexpr int SR = sh_row(DEG);
     constexpr int HALF_ROW = GR / 2; // lanes that own two row elements each
@@ -359,10 +515,20 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     BackwardRay st;
     uint32_t cur = 0;
     float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool replay = tape.pool != nullptr && tape.ctrl[1] == 0u; // grid-uniform
+    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + warp;
+    uint32_t nrec = 0, last_cell = 0;
+    uint2 rec = make_uint2(0u, 0u); // record of the step about to be processed (replay)
     if (!done) {
         backward_ray_setup<DEG>(p, r, ray, sh, st);
         cur = __ldg(p.start + r);
         pc = ldg4(p.cells + cur);
+        if (replay) {
+            uint2 pr = tape.per_ray[r];
+            nrec = pr.x;
+            last_cell = pr.y;
+            done = nrec == 0;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < sh_dim(DEG); ++i)
@@ -370,50 +536,79 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     }
     float t0 = 0.0f;
     uint32_t n = 0;
+    uint32_t next_chunk = 0;
+    if (replay) {
+        next_chunk = tape.table[(uint64_t)gwarp * tape.table_stride]; // chunk of steps 0..31
+        if (!done)
+            rec = tape.pool[(uint64_t)next_chunk * kTapeChunk * 32 + lane];
+    }
 
-    for (;;) {
+    for (uint32_t k = 0;; ++k) {
         bool c_valid = false; // this lane has a (SH, density) row for cell c_cell this iteration
         uint32_t c_cell = kNone;
         float dL_ds = 0.0f;
         float dL_drgb[3] = {0.0f, 0.0f, 0.0f};
 
-        if (!done) {
+        // one step of the ray: (cur, t1, nxt) from the tape, or from scanning the cell's faces
+        bool step = false;
+        float t1 = __int_as_float(0x7f800000);
+        uint32_t nxt = 0;
+        if (replay) {
+            // rolling read: `rec` holds record k (loaded one iteration ago); fetch record k + 1,
+            // whose cell is the cell entered next.  Chunk ids are warp-uniform.
+            if (((k + 1) % kTapeChunk) == 0)
+                next_chunk = tape.table[(uint64_t)gwarp * tape.table_stride + (k + 1) / kTapeChunk];
+            if (!done) {
+                t1 = __uint_as_float(rec.y);
+                if (k + 1 < nrec) {
+                    rec = tape.pool[((uint64_t)next_chunk * kTapeChunk + ((k + 1) % kTapeChunk)) * 32 + lane];
+                    nxt = rec.x;
+                } else {
+                    nxt = last_cell;
+                }
+                step = true;
+            }
+        } else if (!done) {
             n++;
             if (n > p.max_steps) {
                 done = true;
             } else {
                 uint32_t begin, nf;
                 fa.row(cur, begin, nf);
-                float t1 = __int_as_float(0x7f800000);
                 uint32_t face = kNone;
                 fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
                 if (face == kNone) {
                     done = true;
                 } else {
-                    uint32_t nxt = fa.neighbour(begin, face);
-                    float4 pn = ldg4(p.cells + nxt);
-                    if (t1 > t0) {
-                        float rgb[3] = {0.0f, 0.0f, 0.0f};
-                        if (pc.w > 1e-6f)
-                            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * SR, sh, rgb[0], rgb[1], rgb[2]);
-                        float w, fx, fy, fz;
-                        bool flush;
-                        uint32_t flush_idx;
-                        bool go = st.cell(cur, pc, pn, t0, t1, rgb, ray, p.weight_threshold, dL_drgb, dL_ds,
-                                          w, flush, flush_idx, fx, fy, fz);
-                        if (p.point_error)
-                            add_point_error(p, cur, __fmul_rn(w, st.err));
-                        if (flush)
-                            red_add_v4(p.acc + (uint64_t)flush_idx * GR + SR, 0.0f, fx, fy, fz);
-                        c_valid = true;
-                        c_cell = cur;
-                        done = !go;
-                    }
-                    t0 = fmaxf(t0, t1);
-                    cur = nxt;
-                    pc = pn;
+                    nxt = fa.neighbour(begin, face);
+                    step = true;
                 }
             }
+        }
+        if (step) {
+            float4 pn = ldg4(p.cells + nxt);
+            if (t1 > t0) {
+                float rgb[3] = {0.0f, 0.0f, 0.0f};
+                if (pc.w > 1e-6f)
+                    sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * SR, sh, rgb[0], rgb[1], rgb[2]);
+                float w, fx, fy, fz;
+                bool flush;
+                uint32_t flush_idx;
+                bool go = st.cell(cur, pc, pn, t0, t1, rgb, ray, p.weight_threshold, dL_drgb, dL_ds, w,
+                                  flush, flush_idx, fx, fy, fz);
+                if (p.point_error)
+                    add_point_error(p, cur, __fmul_rn(w, st.err));
+                if (flush)
+                    red_add_v4(p.acc + (uint64_t)flush_idx * GR + SR, 0.0f, fx, fy, fz);
+                c_valid = true;
+                c_cell = cur;
+                done = !go;
+            }
+            t0 = fmaxf(t0, t1);
+            cur = nxt;
+            pc = pn;
+            if (replay && k + 1 >= nrec)
+                done = true;
         }
 
         // ---- warp-collective phase: route this iteration's rows

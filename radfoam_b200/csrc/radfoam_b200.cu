@@ -95,6 +95,20 @@ struct rfb_pipeline {
     SceneKey key;
     bool key_valid = false;
     uint32_t acc_points = 0;
+    // walk tape (forward records, backward replays; see foam_kernels.cuh)
+    DeviceBuffer tape_pool, tape_table, tape_per_ray, tape_ctrl;
+    uint32_t tape_capacity = 0;      // chunks
+    uint32_t tape_table_stride = 0;
+    bool tape_valid = false;
+    struct TapeKey {
+        const void *rays = nullptr, *start = nullptr;
+        uint32_t num_rays = 0, image_width = 0, max_steps = 0;
+        float weight_threshold = 0.0f;
+        uint64_t scene_version = 0;
+    } tape_key;
+    uint32_t *tape_readback = nullptr; // pinned host copy of ctrl, refreshed after every recording
+    cudaEvent_t tape_readback_done = nullptr;
+    bool tape_readback_pending = false;
     // optional live kernel timing (rfb_set_profiling): events around the ray kernels
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // fwd start/stop, bwd start/stop
@@ -205,6 +219,54 @@ int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t b
 }
 
 template <typename Faces>
+int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape,
+                          uint32_t blocks, cudaStream_t stream) {
+    switch (deg) {
+    case 0: forward_record_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
+    case 1: forward_record_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
+    case 2: forward_record_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
+    default: forward_record_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
+    }
+    RFB_LAUNCHED();
+    return 0;
+}
+
+// Size / reset the tape for a recording forward of `blocks` CTAs; fills `tape`.
+int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t max_steps, Tape &tape,
+                 cudaStream_t stream) {
+    const uint32_t num_warps = blocks * (kBlock / 32);
+    const uint32_t stride = max_steps / kTapeChunk + 2;
+    // grow the pool if the previous recording needed more chunks than it had
+    if (p->tape_readback_pending && cudaEventQuery(p->tape_readback_done) == cudaSuccess) {
+        p->tape_readback_pending = false;
+        uint32_t wanted = p->tape_readback[0];
+        if (wanted > p->tape_capacity)
+            p->tape_capacity = wanted + wanted / 4;
+    }
+    uint64_t want = (uint64_t)num_warps; // first guess: one chunk (32 steps) per warp; grows on demand
+    if (p->tape_capacity < want)
+        p->tape_capacity = (uint32_t)(want < 0xFFFFFFF0ull ? want : 0xFFFFFFF0ull);
+    const size_t chunk_bytes = (size_t)kTapeChunk * 32 * sizeof(uint2);
+    RFB_CUDA(p->tape_pool.ensure((size_t)p->tape_capacity * chunk_bytes));
+    RFB_CUDA(p->tape_table.ensure((size_t)num_warps * stride * sizeof(uint32_t)));
+    RFB_CUDA(p->tape_per_ray.ensure((size_t)num_rays * sizeof(uint2)));
+    RFB_CUDA(p->tape_ctrl.ensure(4 * sizeof(uint32_t)));
+    RFB_CUDA(cudaMemsetAsync(p->tape_ctrl.ptr, 0, 4 * sizeof(uint32_t), stream));
+    if (!p->tape_readback) {
+        RFB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->tape_readback), 4 * sizeof(uint32_t)));
+        RFB_CUDA(cudaEventCreateWithFlags(&p->tape_readback_done, cudaEventDisableTiming));
+    }
+    p->tape_table_stride = stride;
+    tape.pool = reinterpret_cast<uint2 *>(p->tape_pool.ptr);
+    tape.table = reinterpret_cast<uint32_t *>(p->tape_table.ptr);
+    tape.per_ray = reinterpret_cast<uint2 *>(p->tape_per_ray.ptr);
+    tape.ctrl = reinterpret_cast<uint32_t *>(p->tape_ctrl.ptr);
+    tape.capacity = p->tape_capacity;
+    tape.table_stride = stride;
+    return 0;
+}
+
+template <typename Faces>
 int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
                     cudaStream_t stream) {
     switch (deg) {
@@ -218,8 +280,8 @@ int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t
 }
 
 template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
-int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, uint32_t blocks,
-                               cudaStream_t stream) {
+int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const Tape &tape,
+                               uint32_t blocks, cudaStream_t stream) {
     constexpr int GR = grad_row(DEG);
     constexpr size_t smem = (size_t)(kBlock / 32) * (32 * GR + SLOTS * GR + SLOTS) * sizeof(float);
     auto kernel = backward_cached_kernel<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS>;
@@ -228,37 +290,37 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, uint32
         RFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kernel<<<blocks, kBlock, smem, stream>>>(bp, fa);
+    kernel<<<blocks, kBlock, smem, stream>>>(bp, fa, tape);
     RFB_LAUNCHED();
     return 0;
 }
 
 template <int DEG, typename Faces>
-int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
-                               cudaStream_t stream) {
+int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, const Tape &tape,
+                               uint32_t blocks, cudaStream_t stream) {
     // Shipped configuration: 8 cache slots per warp, groups of >= 8 lanes go through the
     // cache, 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200):
     // direct 29.3 ms; (32 slots, >=2, 4 CTAs) 21.5; (16, >=4, 5) 17.7; (16, >=8, 5) 16.6;
     // (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower (profiles/r01_backward_variants.json).
     // RFB_BWD_VARIANT selects the neighbours kept for re-tuning on other scenes.
     switch (variant) {
-    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 12, 5>(bp, fa, blocks, stream);
-    case 2: return launch_backward_cached_cfg<DEG, Faces, 4, 8, 5>(bp, fa, blocks, stream);
-    case 3: return launch_backward_cached_cfg<DEG, Faces, 8, 6, 5>(bp, fa, blocks, stream);
-    default: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, blocks, stream);
+    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 12, 5>(bp, fa, tape, blocks, stream);
+    case 2: return launch_backward_cached_cfg<DEG, Faces, 4, 8, 5>(bp, fa, tape, blocks, stream);
+    case 3: return launch_backward_cached_cfg<DEG, Faces, 8, 6, 5>(bp, fa, tape, blocks, stream);
+    default: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, tape, blocks, stream);
     }
 }
 
 template <typename Faces>
-int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
-                           cudaStream_t stream) {
+int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, const Tape &tape,
+                           uint32_t blocks, cudaStream_t stream) {
     const char *v = getenv("RFB_BWD_VARIANT");
     int variant = v ? atoi(v) : 0;
     switch (deg) {
-    case 0: return launch_backward_cached_deg<0>(0, bp, fa, blocks, stream);
-    case 1: return launch_backward_cached_deg<1>(0, bp, fa, blocks, stream);
-    case 2: return launch_backward_cached_deg<2>(0, bp, fa, blocks, stream);
-    default: return launch_backward_cached_deg<3>(variant, bp, fa, blocks, stream);
+    case 0: return launch_backward_cached_deg<0>(0, bp, fa, tape, blocks, stream);
+    case 1: return launch_backward_cached_deg<1>(0, bp, fa, tape, blocks, stream);
+    case 2: return launch_backward_cached_deg<2>(0, bp, fa, tape, blocks, stream);
+    default: return launch_backward_cached_deg<3>(variant, bp, fa, tape, blocks, stream);
     }
 }
 
@@ -316,6 +378,14 @@ void rfb_destroy_pipeline(rfb_pipeline *p) {
     p->faces.release();
     p->nbr.release();
     p->acc.release();
+    p->tape_pool.release();
+    p->tape_table.release();
+    p->tape_per_ray.release();
+    p->tape_ctrl.release();
+    if (p->tape_readback)
+        cudaFreeHost(p->tape_readback);
+    if (p->tape_readback_done)
+        cudaEventDestroy(p->tape_readback_done);
     for (auto &e : p->ev)
         if (e)
             cudaEventDestroy(e);
@@ -328,6 +398,19 @@ uint32_t rfb_grad_row_floats(const rfb_pipeline *p) { return p ? (uint32_t)rfb::
 void rfb_invalidate_cache(rfb_pipeline *p) {
     if (p)
         p->key_valid = false;
+}
+
+int rfb_tape_status(rfb_pipeline *p, uint32_t *capacity_chunks, uint32_t *used_chunks,
+                    uint32_t *overflowed) {
+    if (!p || !capacity_chunks || !used_chunks || !overflowed)
+        return fail("rfb_tape_status: NULL argument");
+    if (!p->tape_valid || !p->tape_readback)
+        return fail("rfb_tape_status: no recorded tape");
+    RFB_CUDA(cudaEventSynchronize(p->tape_readback_done));
+    *capacity_chunks = p->tape_capacity;
+    *used_chunks = p->tape_readback[0];
+    *overflowed = p->tape_readback[1];
+    return 0;
 }
 
 void rfb_set_profiling(rfb_pipeline *p, int enabled) {
@@ -406,11 +489,34 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
     fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
     fa.off = point_adjacency_offsets;
+    const bool record = opts && (opts->flags & RFB_FLAG_RECORD_TAPE) && opts->scene_version != 0;
+    p->tape_valid = false;
+    Tape tape = {};
+    if (record)
+        if (int rc = prepare_tape(p, blocks, num_rays, s.max_intersections, tape, stream))
+            return rc;
     if (int rc = profile_mark(p, 0, stream))
         return rc;
-    if (int rc = launch_forward(p->sh_degree, fp, fa, blocks, stream))
+    if (int rc = record ? launch_forward_record(p->sh_degree, fp, fa, tape, blocks, stream)
+                        : launch_forward(p->sh_degree, fp, fa, blocks, stream))
         return rc;
-    return profile_mark(p, 1, stream);
+    if (int rc = profile_mark(p, 1, stream))
+        return rc;
+    if (record) {
+        RFB_CUDA(cudaMemcpyAsync(p->tape_readback, p->tape_ctrl.ptr, 2 * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, stream));
+        RFB_CUDA(cudaEventRecord(p->tape_readback_done, stream));
+        p->tape_readback_pending = true;
+        p->tape_key.rays = rays;
+        p->tape_key.start = start_point_index;
+        p->tape_key.num_rays = num_rays;
+        p->tape_key.image_width = fp.image_width;
+        p->tape_key.max_steps = s.max_intersections;
+        p->tape_key.weight_threshold = s.weight_threshold;
+        p->tape_key.scene_version = opts->scene_version;
+        p->tape_valid = true;
+    }
+    return 0;
 }
 
 int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *settings,
@@ -472,7 +578,22 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
         return rc;
     const char *mode = getenv("RFB_BWD_MODE"); // "direct" | "cached" (experiment switch)
     bool cached = mode ? strcmp(mode, "direct") != 0 : true;
-    if (int rc = cached ? launch_backward_cached(p->sh_degree, bp, fa, blocks, stream)
+    // replay the forward's walk tape when the caller vouches the inputs are those of the last
+    // recording forward (and everything the walk depends on matches)
+    Tape tape = {};
+    const rfb_pipeline::TapeKey &tk = p->tape_key;
+    if (cached && opts && (opts->flags & RFB_FLAG_USE_TAPE) && p->tape_valid && opts->scene_version != 0 &&
+        tk.scene_version == opts->scene_version && tk.rays == rays && tk.start == start_point_index &&
+        tk.num_rays == num_rays && tk.image_width == bp.image_width && tk.max_steps == s.max_intersections &&
+        tk.weight_threshold == s.weight_threshold) {
+        tape.pool = reinterpret_cast<uint2 *>(p->tape_pool.ptr);
+        tape.table = reinterpret_cast<uint32_t *>(p->tape_table.ptr);
+        tape.per_ray = reinterpret_cast<uint2 *>(p->tape_per_ray.ptr);
+        tape.ctrl = reinterpret_cast<uint32_t *>(p->tape_ctrl.ptr);
+        tape.capacity = p->tape_capacity;
+        tape.table_stride = p->tape_table_stride;
+    }
+    if (int rc = cached ? launch_backward_cached(p->sh_degree, bp, fa, tape, blocks, stream)
                         : launch_backward(p->sh_degree, bp, fa, blocks, stream))
         return rc;
     return profile_mark(p, 3, stream);

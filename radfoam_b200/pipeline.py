@@ -57,6 +57,10 @@ class Pipeline:
         self.cache_scene = True
         self._scene_refs = None
         self._scene_version = 0
+        # walk tape: a forward whose scene inputs require grad records (cell, t1) per step so the
+        # backward of the same step replays it instead of re-scanning faces
+        self.record_tape = True
+        self._tape_refs = None
 
     def __del__(self):
         try:
@@ -89,6 +93,14 @@ class Pipeline:
         _lib.check(self._lib.rfb_last_kernel_ms(self._handle, {"forward": 0, "backward": 1}[which],
                                                 ctypes.byref(ms)))
         return float(ms.value)
+
+    def tape_status(self) -> dict:
+        """Walk-tape pool state after the last recording forward (synchronises on it)."""
+        cap, used, over = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        _lib.check(self._lib.rfb_tape_status(self._handle, ctypes.byref(cap), ctypes.byref(used),
+                                             ctypes.byref(over)))
+        return {"capacity_chunks": cap.value, "used_chunks": used.value, "overflowed": bool(over.value),
+                "bytes": used.value * 8192}
 
     def invalidate_cache(self) -> None:
         self._scene_refs = None
@@ -138,6 +150,14 @@ class Pipeline:
             raise RuntimeError("start_point must have uint32 dtype")
         if start_point.device.type != "cuda":
             raise RuntimeError("start_point must be on CUDA device")
+
+    def _tape_flag(self, rays_c, start_c, scene_version) -> int:
+        """FLAG_USE_TAPE iff these are the very tensors (unmodified) of the last recording forward."""
+        refs = self._tape_refs
+        if not refs or refs[2] != scene_version or scene_version == 0:
+            return 0
+        same = all(r() is t and v == t._version for (r, v), t in zip(refs[:2], (rays_c, start_c)))
+        return _lib.FLAG_USE_TAPE if same else 0
 
     def _settings(self, weight_threshold, max_intersections):
         s = _lib.TraceSettings(0.001, 1024)  # default_trace_settings(), pipeline.h:15-20
@@ -203,7 +223,12 @@ class Pipeline:
             depth = torch.empty(batch + [num_q], dtype=torch.float32, device=dev)
             depth_indices = torch.empty(batch + [num_q], dtype=torch.uint32, device=dev)
 
-        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c)
+        record = (self.record_tape and self.cache_scene
+                  and (points.requires_grad or attributes.requires_grad))
+        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c,
+                          _lib.FLAG_RECORD_TAPE if record else 0)
+        self._tape_refs = ([(weakref.ref(t), t._version) for t in (rays_c, start_c)]
+                           + [opts.scene_version] if record else None)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(self._lib.rfb_trace_forward(
@@ -322,6 +347,7 @@ class Pipeline:
 
         opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c,
                           _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0)
+        opts.flags |= self._tape_flag(rays_c, start_c, opts.scene_version)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(self._lib.rfb_trace_backward(
@@ -355,6 +381,7 @@ class Pipeline:
         if err_c is not None:
             point_error = torch.zeros((num_points, 1), dtype=self._dtype, device=dev)
         opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c)
+        opts.flags |= self._tape_flag(rays_c, start_c, opts.scene_version)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(self._lib.rfb_trace_backward_accumulate(

@@ -29,7 +29,7 @@ def to_dev(torch, a):
 
 
 def run_ours(torch, case, attr_dtype="float32", weight_threshold=None, max_intersections=None,
-             return_contribution=False, flat=False, backward=True, ray_error=None):
+             return_contribution=False, flat=False, backward=True, ray_error=None, tape=False, repeat=1):
     import radfoam_b200
 
     f = case.foam
@@ -45,19 +45,24 @@ def run_ours(torch, case, attr_dtype="float32", weight_threshold=None, max_inter
         g = g.reshape(-1, 4)
         gd = None if gd is None else gd.reshape(-1, gd.shape[-1])
     scene = [to_dev(torch, x) for x in (f.points, attrs, f.adjacency, f.offsets)]
+    if tape:  # scene tensors that require grad make the forward record the walk tape
+        scene[0].requires_grad_(True)
+        scene[1].requires_grad_(True)
+    pipe.record_tape = tape
     rays_d, start_d, dq_d = to_dev(torch, rays), to_dev(torch, start), to_dev(torch, dq)
-    fwd = pipe.trace_forward(*scene, rays_d, start_d, depth_quantiles=dq_d,
-                             weight_threshold=weight_threshold, max_intersections=max_intersections,
-                             return_contribution=return_contribution)
-    out = {k: v.cpu().numpy() for k, v in fwd.items()}
-    if backward:
-        g_d = to_dev(torch, g.astype(np.float16) if half else g)
-        err_d = to_dev(torch, ray_error)
-        bwd = pipe.trace_backward(*scene, rays_d, start_d, fwd["rgba"], g_d, dq_d,
-                                  fwd.get("depth_indices"), to_dev(torch, gd), err_d,
-                                  weight_threshold=weight_threshold, max_intersections=max_intersections)
-        out.update({k: v.cpu().numpy() for k, v in bwd.items() if k != "ray_grad"})
-    torch.cuda.synchronize()
+    for _ in range(repeat):
+        fwd = pipe.trace_forward(*scene, rays_d, start_d, depth_quantiles=dq_d,
+                                 weight_threshold=weight_threshold, max_intersections=max_intersections,
+                                 return_contribution=return_contribution)
+        out = {k: v.cpu().numpy() for k, v in fwd.items()}
+        if backward:
+            g_d = to_dev(torch, g.astype(np.float16) if half else g)
+            err_d = to_dev(torch, ray_error)
+            bwd = pipe.trace_backward(*scene, rays_d, start_d, fwd["rgba"], g_d, dq_d,
+                                      fwd.get("depth_indices"), to_dev(torch, gd), err_d,
+                                      weight_threshold=weight_threshold, max_intersections=max_intersections)
+            out.update({k: v.cpu().numpy() for k, v in bwd.items() if k != "ray_grad"})
+        torch.cuda.synchronize()
     return out
 
 
@@ -285,6 +290,77 @@ def test_trace_benchmark(torch_cuda, model, attr_dtype):
     assert np.abs(a - b).max() <= 1
     assert (a != b).any(axis=-1).mean() < 2e-3
     assert (b[..., :3].sum(axis=-1) > 0).mean() > 0.2  # the frame is not empty
+
+
+# ------------------------------------------------------------------ walk tape (record / replay)
+@pytest.mark.parametrize("make_case", [lambda: common.config1(3, 2),
+                                       lambda: common.scene_case(num_points=60000, width=320, height=200),
+                                       lambda: common.scene_case(num_points=60000, width=320, height=200, inside=True),
+                                       lambda: common.random_ray_case(num_points=60000, num_rays=100000)],
+                         ids=["config1", "scene", "scene_inside", "random_batch"])
+def test_tape_replay_matches_reference_kernels(torch_cuda, make_case):
+    """Forward that records the tape == plain forward bit for bit; backward that replays it ==
+    the reference's re-walk backward."""
+    case = make_case()
+    got = run_ours(torch_cuda, case, tape=True)
+    plain = run_ours(torch_cuda, case, tape=False)
+    for k in ("rgba", "depth", "depth_indices", "num_intersections"):
+        assert np.array_equal(got[k], plain[k]), k
+    ref = run_ref_gpu(torch_cuda, case)
+    assert_forward_equal(got, ref)
+    assert_grads_close(got, ref)
+
+
+def test_tape_overflow_falls_back_then_grows(torch_cuda):
+    """The tape pool starts at one 32-step chunk per warp; this scene needs two.  First step:
+    the pool overflows and the backward re-walks; the pool then grows and later steps replay.
+    Every step must equal the reference's kernels."""
+    import radfoam_b200
+
+    torch = torch_cuda
+    case = common.scene_case(num_points=60000, width=320, height=200, inside=True)
+    ref = run_ref_gpu(torch, case)
+    assert ref["num_intersections"].max() > 40
+    f = case.foam
+    pipe = radfoam_b200.create_pipeline(3)
+    scene = [to_dev(torch, x) for x in (f.points, f.attributes, f.adjacency, f.offsets)]
+    scene[0].requires_grad_(True)
+    rays, start, dq = to_dev(torch, case.rays), to_dev(torch, case.start), to_dev(torch, case.quantiles)
+    g, gd = to_dev(torch, case.grad_rgba), to_dev(torch, case.grad_depth)
+    overflowed = []
+    for step in range(3):
+        fwd = pipe.trace_forward(*scene, rays, start, depth_quantiles=dq)
+        overflowed.append(pipe.tape_status()["overflowed"])
+        bwd = pipe.trace_backward(*scene, rays, start, fwd["rgba"], g, dq, fwd["depth_indices"], gd)
+        got = {k: v.cpu().numpy() for k, v in list(fwd.items()) + list(bwd.items()) if k != "ray_grad"}
+        assert_forward_equal(got, ref)
+        assert_grads_close(got, ref)
+    assert overflowed[0] and not overflowed[-1], overflowed
+    st = pipe.tape_status()
+    assert st["used_chunks"] <= st["capacity_chunks"]
+
+
+def test_tape_is_not_replayed_for_other_rays(torch_cuda):
+    """The tape is keyed on the ray / start tensors: a backward on different rays must re-walk."""
+    import radfoam_b200
+
+    torch = torch_cuda
+    case = common.scene_case()
+    f = case.foam
+    pipe = radfoam_b200.create_pipeline(3)
+    scene = [to_dev(torch, x) for x in (f.points, f.attributes, f.adjacency, f.offsets)]
+    scene[0].requires_grad_(True)
+    rays, start, dq = to_dev(torch, case.rays), to_dev(torch, case.start), to_dev(torch, case.quantiles)
+    g, gd = to_dev(torch, case.grad_rgba), to_dev(torch, case.grad_depth)
+    fwd = pipe.trace_forward(*scene, rays, start, depth_quantiles=dq)
+    # same values, different tensors, mirrored image: must not use the tape of `rays`
+    rays2, start2, dq2, g2, gd2 = [t.flip(1).contiguous() for t in (rays, start, dq, g, gd)]
+    fwd2 = {k: v.flip(1).contiguous() for k, v in fwd.items() if k in ("rgba", "depth_indices")}
+    a = pipe.trace_backward(*scene, rays2, start2, fwd2["rgba"], g2, dq2, fwd2["depth_indices"], gd2)
+    b = pipe.trace_backward(*scene, rays, start, fwd["rgba"], g, dq, fwd["depth_indices"], gd)
+    torch.cuda.synchronize()
+    assert common.grad_error(a["attr_grad"].cpu().numpy(), b["attr_grad"].cpu().numpy()) < 1e-5
+    assert common.grad_error(a["points_grad"].cpu().numpy(), b["points_grad"].cpu().numpy()) < 1e-5
 
 
 # ------------------------------------------------------------------ invariants

@@ -20,6 +20,7 @@ d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
 scene = [d(x) for x in (f.points, f.attributes, f.adjacency, f.offsets)]
 fr = {k: d(v) for k, v in frame.items()}
 pipe = radfoam_b200.create_pipeline(3)
+pipe.record_tape = False
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res = {"fwd_ms": timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))}
 
@@ -39,6 +40,16 @@ for v in range(4):
     err = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
     res[f"cached_v{v}_ms"] = timeit(bwd)
     res[f"cached_v{v}_err_vs_direct"] = err
+# walk tape: recording forward + replaying backward
+scene[0].requires_grad_(True)
+pipe.record_tape = True
+os.environ["RFB_BWD_VARIANT"] = "0"
+fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
+out = bwd()
+res["tape_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
+res["fwd_record_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
+fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
+res["bwd_replay_ms"] = timeit(bwd)
 print(json.dumps(res, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/variant_bench.json", "w"), indent=1)
