@@ -129,12 +129,20 @@ def measured_peak_hbm():
 
 
 def algorithmic_bytes(num_steps: int, num_rays: int, mean_degree: float, attr_dim: int, q: int):
-    """SURVEY.md §8(d) no-reuse gather model, fp32 attributes (s = 4)."""
+    """Bytes each ray kernel has to touch under SURVEY.md §8(d)'s no-reuse gather model, fp32
+    attributes (s = 4), stated per ray-step and per ray:
+      forward  (records the tape): offsets 8 + faces 8*deg + neighbour 4 + next point/density 16
+                                   + attribute row s*(A-1) + tape record 8
+      backward (replays the tape): tape record 8 + next point/density 16 + attribute row s*(A-1)
+                                   + gradient row read-modify-write counted once s*A + position
+                                   gradient 12
+    The reference's re-walk backward would be forward + s*A + 12 = 551 B; replaying the tape
+    removes the face and offset reads from the backward."""
     s = 4
-    b_f = 8 + 8 * mean_degree + 4 + 12 + s * attr_dim          # per ray-step, forward
-    b_b = b_f + s * attr_dim + 12                              # per ray-step, backward
-    fixed_f = 24 + 4 + 4 * s + 4 + q * 12
-    fixed_b = 24 + 4 + 4 * s + 4 * s + q * 12
+    b_f = 8 + 8 * mean_degree + 4 + 16 + s * (attr_dim - 1) + 8
+    b_b = 8 + 16 + s * (attr_dim - 1) + s * attr_dim + 12
+    fixed_f = 24 + 4 + 4 * s + 4 + q * 12 + 8
+    fixed_b = 24 + 4 + 4 * s + 4 * s + q * 12 + 8
     return (num_steps * b_f + num_rays * fixed_f, num_steps * b_b + num_rays * fixed_b, b_f, b_b)
 
 
@@ -379,7 +387,12 @@ def run_ours(args):
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "bytes_per_ray_step": {"forward": b_f, "backward": b_b},
-                     "ray_steps_per_launch": steps_local},
+                     "ray_steps_per_launch": steps_local,
+                     "note": "achieved = no-reuse algorithmic bytes / kernel time (an EFFECTIVE rate: "
+                             "neighbouring rays re-touch the same cells in L1/L2, so it may exceed the HBM "
+                             "peak); traffic = DRAM bytes ncu measured for the same launch "
+                             "(profiles/traffic.json). The kernels are issue / L2-atomic bound, not DRAM "
+                             "bound: see the ncu summaries under profiles/."},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -486,11 +486,19 @@ __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p
 // MIN_GROUP: smallest same-cell lane group routed through the cache (smaller groups reduce
 // directly: all such lanes issue their 13 reductions simultaneously, which costs fewer issue
 // slots than one serial cache round per group, at the price of more L2 atomic traffic).
-// `tape.pool != nullptr`: replay the forward's record of (cell, t1) instead of re-scanning faces
-// (falls back to the re-walk, uniformly for the whole grid, if the tape overflowed).
-template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
+// REPLAY = true: the steps come from the forward's tape of (cell, t1) instead of re-scanning
+// faces.  When a tape is offered the host launches both instantiations back to back; each looks
+// at the tape's overflow flag first and exactly one of them does the work (the other returns at
+// once), so a pool overflow needs no host round trip.  (Prefetching the next cell's SH row into
+// L1 or L2 as soon as the cell is known was tried and is no faster: 11.8 vs 11.65 ms.)
+template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS, bool REPLAY>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     backward_cached_kernel(const BackwardParams p, const Faces fa, const Tape tape) {
+    if (tape.pool != nullptr) {
+        const bool overflowed = tape.ctrl[1] != 0u;
+        if (REPLAY == overflowed) // replay kernel on an overflowed tape / re-walk kernel on a good one
+            return;
+    }
     constexpr int GR = grad_row(DEG);
     constexpr int SR = sh_row(DEG);
     constexpr int HALF_ROW = GR / 2; // lanes that own two row elements each
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     BackwardRay st;
     uint32_t cur = 0;
     float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool replay = tape.pool != nullptr && tape.ctrl[1] == 0u; // grid-uniform
+    constexpr bool replay = REPLAY;
     const uint32_t gwarp = blockIdx.x * (kBlock / 32) + warp;
     uint32_t nrec = 0, last_cell = 0;
     uint2 rec = make_uint2(0u, 0u); // record of the step about to be processed (replay)
@@ -536,11 +544,23 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     }
     float t0 = 0.0f;
     uint32_t n = 0;
-    uint32_t next_chunk = 0;
+    // replay pipeline: records k and k+1 are kept in registers and record k+2 is requested
+    // while step k is processed, so the streamed tape read is never waited for.  (Also
+    // prefetching the cell gather one step ahead costs 8 more registers, spills, and is slower:
+    // 12.5 vs 11.6 ms.)
+    uint32_t chunk_ahead = 0; // chunk id (warp-uniform) of tape row k + 2
+    uint2 recB = make_uint2(0u, 0u);
+    auto tape_row = [&](uint32_t chunk_id, uint32_t j) -> uint2 {
+        // record j of this lane; past the end: the cell the forward stopped in
+        return j < nrec ? tape.pool[((uint64_t)chunk_id * kTapeChunk + (j % kTapeChunk)) * 32 + lane]
+                        : make_uint2(last_cell, 0u);
+    };
     if (replay) {
-        next_chunk = tape.table[(uint64_t)gwarp * tape.table_stride]; // chunk of steps 0..31
-        if (!done)
-            rec = tape.pool[(uint64_t)next_chunk * kTapeChunk * 32 + lane];
+        chunk_ahead = tape.table[(uint64_t)gwarp * tape.table_stride]; // rows 0..31
+        if (!done) {
+            rec = tape_row(chunk_ahead, 0);
+            recB = tape_row(chunk_ahead, 1);
+        }
     }
 
     for (uint32_t k = 0;; ++k) {
@@ -554,18 +574,14 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
         float t1 = __int_as_float(0x7f800000);
         uint32_t nxt = 0;
         if (replay) {
-            // rolling read: `rec` holds record k (loaded one iteration ago); fetch record k + 1,
-            // whose cell is the cell entered next.  Chunk ids are warp-uniform.
-            if (((k + 1) % kTapeChunk) == 0)
-                next_chunk = tape.table[(uint64_t)gwarp * tape.table_stride + (k + 1) / kTapeChunk];
+            if (((k + 2) % kTapeChunk) == 0)
+                chunk_ahead = tape.table[(uint64_t)gwarp * tape.table_stride + (k + 2) / kTapeChunk];
             if (!done) {
+                uint2 recC = tape_row(chunk_ahead, k + 2);
                 t1 = __uint_as_float(rec.y);
-                if (k + 1 < nrec) {
-                    rec = tape.pool[((uint64_t)next_chunk * kTapeChunk + ((k + 1) % kTapeChunk)) * 32 + lane];
-                    nxt = rec.x;
-                } else {
-                    nxt = last_cell;
-                }
+                nxt = recB.x;
+                rec = recB;
+                recB = recC;
                 step = true;
             }
         } else if (!done) {
@@ -639,13 +655,25 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
                 todo &= ~gmask;
                 float a0 = 0.0f, a1 = 0.0f;
                 if (lane < HALF_ROW) {
+                    // four staged rows per round: the loads are issued together so their
+                    // shared-memory latency overlaps (groups have >= MIN_GROUP members)
+                    const float *col = stage + 2 * lane;
                     unsigned m = gmask;
                     while (m) {
-                        int src = __ffs(m) - 1;
+                        int s0 = __ffs(m) - 1;
                         m &= m - 1;
-                        float2 v = *reinterpret_cast<const float2 *>(stage + src * GR + 2 * lane);
-                        a0 += v.x;
-                        a1 += v.y;
+                        int s1 = m ? __ffs(m) - 1 : -1;
+                        m &= m - 1;
+                        int s2 = m ? __ffs(m) - 1 : -1;
+                        m &= m - 1;
+                        int s3 = m ? __ffs(m) - 1 : -1;
+                        m &= m - 1;
+                        float2 v0 = *reinterpret_cast<const float2 *>(col + s0 * GR);
+                        float2 v1 = s1 >= 0 ? *reinterpret_cast<const float2 *>(col + s1 * GR) : make_float2(0.f, 0.f);
+                        float2 v2 = s2 >= 0 ? *reinterpret_cast<const float2 *>(col + s2 * GR) : make_float2(0.f, 0.f);
+                        float2 v3 = s3 >= 0 ? *reinterpret_cast<const float2 *>(col + s3 * GR) : make_float2(0.f, 0.f);
+                        a0 += (v0.x + v1.x) + (v2.x + v3.x);
+                        a1 += (v0.y + v1.y) + (v2.y + v3.y);
                     }
                 }
                 uint32_t slot = (lc * 2654435761u) >> (32 - __builtin_ctz(SLOTS));

@@ -279,12 +279,12 @@ int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t
     return 0;
 }
 
-template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
-int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const Tape &tape,
+template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS, bool REPLAY>
+int launch_backward_cached_one(const BackwardParams &bp, const Faces &fa, const Tape &tape,
                                uint32_t blocks, cudaStream_t stream) {
     constexpr int GR = grad_row(DEG);
     constexpr size_t smem = (size_t)(kBlock / 32) * (32 * GR + SLOTS * GR + SLOTS) * sizeof(float);
-    auto kernel = backward_cached_kernel<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS>;
+    auto kernel = backward_cached_kernel<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS, REPLAY>;
     static bool configured = false; // per instantiation; the attribute is idempotent
     if (!configured) {
         RFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -295,18 +295,31 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const 
     return 0;
 }
 
+// With a tape: the replay kernel and the re-walk kernel are both launched; the tape's overflow
+// flag (device side) decides which one works.  Without: the re-walk kernel alone.
+template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS>
+int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const Tape &tape,
+                               uint32_t blocks, cudaStream_t stream) {
+    if (tape.pool)
+        if (int rc = launch_backward_cached_one<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS, true>(
+                bp, fa, tape, blocks, stream))
+            return rc;
+    return launch_backward_cached_one<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS, false>(bp, fa, tape, blocks,
+                                                                                     stream);
+}
+
 template <int DEG, typename Faces>
 int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, const Tape &tape,
                                uint32_t blocks, cudaStream_t stream) {
     // Shipped configuration: 8 cache slots per warp, groups of >= 8 lanes go through the
-    // cache, 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200):
-    // direct 29.3 ms; (32 slots, >=2, 4 CTAs) 21.5; (16, >=4, 5) 17.7; (16, >=8, 5) 16.6;
-    // (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower (profiles/r01_backward_variants.json).
-    // RFB_BWD_VARIANT selects the neighbours kept for re-tuning on other scenes.
+    // cache, 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200),
+    // re-walk backward: direct 29.3 ms; (32 slots, >=2, 4 CTAs) 21.5; (16, >=4, 5) 17.7;
+    // (16, >=8, 5) 16.6; (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower
+    // (profiles/r01_backward_variants.json).  RFB_BWD_VARIANT selects neighbours for re-tuning.
     switch (variant) {
-    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 12, 5>(bp, fa, tape, blocks, stream);
-    case 2: return launch_backward_cached_cfg<DEG, Faces, 4, 8, 5>(bp, fa, tape, blocks, stream);
-    case 3: return launch_backward_cached_cfg<DEG, Faces, 8, 6, 5>(bp, fa, tape, blocks, stream);
+    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 4, 5>(bp, fa, tape, blocks, stream);
+    case 2: return launch_backward_cached_cfg<DEG, Faces, 8, 12, 5>(bp, fa, tape, blocks, stream);
+    case 3: return launch_backward_cached_cfg<DEG, Faces, 16, 8, 5>(bp, fa, tape, blocks, stream);
     default: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, tape, blocks, stream);
     }
 }

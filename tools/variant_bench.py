@@ -34,22 +34,21 @@ os.environ["RFB_BWD_MODE"] = "direct"
 base = bwd()
 res["direct_ms"] = timeit(bwd)
 os.environ["RFB_BWD_MODE"] = "cached"
-for v in range(4):
-    os.environ["RFB_BWD_VARIANT"] = str(v)
-    out = bwd()
-    err = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
-    res[f"cached_v{v}_ms"] = timeit(bwd)
-    res[f"cached_v{v}_err_vs_direct"] = err
+os.environ["RFB_BWD_VARIANT"] = "0"
+out = bwd()
+res["rewalk_v0_ms"] = timeit(bwd)
 # walk tape: recording forward + replaying backward
 scene[0].requires_grad_(True)
 pipe.record_tape = True
-os.environ["RFB_BWD_VARIANT"] = "0"
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
-out = bwd()
-res["tape_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
 res["fwd_record_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
-res["bwd_replay_ms"] = timeit(bwd)
+res["tape"] = pipe.tape_status()
+for v in range(4):
+    os.environ["RFB_BWD_VARIANT"] = str(v)
+    out = bwd()
+    res[f"replay_v{v}_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
+    res[f"replay_v{v}_ms"] = timeit(bwd)
 print(json.dumps(res, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/variant_bench.json", "w"), indent=1)
