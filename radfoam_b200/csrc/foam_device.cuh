@@ -291,24 +291,57 @@ struct CallerFaces {
         begin = a;
         nf = b - a;
     }
+    // the reference's loop verbatim (exact IEEE quotient per face)
+    __device__ __forceinline__ void scan_exact(uint32_t begin, uint32_t nf, float px, float py,
+                                               float pz, const RayGeom &ray, float &t1,
+                                               uint32_t &face) const {
+        const uint2 *p = faces + begin;
+        for (uint32_t f = 0; f < nf; ++f) {
+            float t, dp;
+            walk_face(ldg2(p + f), px, py, pz, ray, t, dp);
+            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
+        }
+    }
+    // ranked scan, same argument and same fallbacks as PaddedFaces::scan
     __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
                                          const RayGeom &ray, float &t1, uint32_t &face) const {
+        const float kInf = __int_as_float(0x7f800000);
         const uint2 *p = faces + begin;
+        float best = kInf, second = kInf;
+        uint32_t bf = kNone;
+        bool any_front = false;
+        auto rank = [&](uint2 rec, uint32_t idx) {
+            float num, dp;
+            walk_face_parts(rec, px, py, pz, ray, num, dp);
+            float q = num * rcp_approx(dp);
+            bool front = dp > 0.0f;
+            any_front |= front;
+            q = front ? q : kInf;
+            bf = (q < best) ? idx : bf;
+            second = fminf(second, fmaxf(best, q));
+            best = fminf(best, q);
+        };
         uint32_t f = 0;
         for (; f + 2 <= nf; f += 2) {
             uint2 a = ldg2(p + f);
             uint2 b = ldg2(p + f + 1);
-            float t, dp;
-            walk_face(a, px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
-            walk_face(b, px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1) { t1 = t; face = f + 1; }
+            rank(a, f);
+            rank(b, f + 1);
         }
-        if (f < nf) {
-            uint2 a = ldg2(p + f);
+        if (f < nf)
+            rank(ldg2(p + f), f);
+        if (!any_front)
+            return; // unbounded hull cell: no face, t1 stays +inf
+        float ab = fabsf(best);
+        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
+        bool clear = (second - best) > margin;
+        if (clear && ab < 1e30f) {
             float t, dp;
-            walk_face(a, px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
+            walk_face(ldg2(p + bf), px, py, pz, ray, t, dp);
+            t1 = t;
+            face = bf;
+        } else {
+            scan_exact(begin, nf, px, py, pz, ray, t1, face);
         }
     }
     __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {

@@ -65,10 +65,37 @@ def test_missing_library_is_a_hard_error(monkeypatch):
 
 
 def test_product_never_imports_the_oracle():
+    """oracle/ is a checker: nothing under radfoam_b200/ may import, link or call it."""
     pkg = os.path.join(ROOT, "radfoam_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("oracle/_ref", "").lower() or f == "__init__.py" and False, \
-                    f"{f} mentions the oracle"
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "radfoam_oracle" not in text and "libradfoam_ref" not in text, f
+
+
+def test_pipeline_methods_take_the_reference_binding_arguments():
+    """Argument names / order / defaults of the pybind11 Pipeline the reference's Python code calls
+    (torch_bindings/pipeline_bindings.cpp:626-672), so radfoam_model/render.py:33-42, 80-93 and
+    benchmark.py:99-108 work unchanged against this class."""
+    import inspect
+
+    from radfoam_b200.pipeline import Pipeline, create_pipeline
+
+    def names(fn):
+        return [p.name for p in inspect.signature(fn).parameters.values()][1:]
+
+    assert names(Pipeline.trace_forward) == [
+        "points", "attributes", "point_adjacency", "point_adjacency_offsets", "rays", "start_point",
+        "depth_quantiles", "weight_threshold", "max_intersections", "return_contribution"]
+    assert names(Pipeline.trace_backward)[:14] == [
+        "points", "attributes", "point_adjacency", "point_adjacency_offsets", "rays", "start_point",
+        "rgb_out", "grad_in", "depth_quantiles", "depth_indices", "depth_grad_in", "ray_error",
+        "weight_threshold", "max_intersections"]
+    assert names(Pipeline.trace_benchmark) == [
+        "points", "attributes", "point_adjacency", "point_adjacency_offsets", "adjacent_diff", "camera",
+        "start_point", "output_rgba", "weight_threshold", "max_intersections"]
+    sig = inspect.signature(Pipeline.trace_forward).parameters
+    assert sig["depth_quantiles"].default is None and sig["return_contribution"].default is False
+    assert inspect.signature(create_pipeline).parameters["attr_dtype"].default == "float32"
