@@ -75,47 +75,57 @@ def make_frame(f, width: int, height: int):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, every few
+    milliseconds from a thread: the timed region of a short run is only tens of milliseconds)."""
 
-    def __init__(self, index: int):
-        self.proc = None
+    def __init__(self, index: int, period_s: float = 0.004):
+        import threading
+
+        self.samples, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = int(get_reasons(h))
+                        for n, bit in names.items():
+                            if mask & bit:
+                                self.reasons.add(n)
+                    except Exception as e:  # noqa: BLE001
+                        self.err = repr(e)
+                        return
+                    self._stop.wait(period_s)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in out.strip().splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+               "sm_max_mhz": self.max_mhz, "samples": len(self.samples), "reasons": sorted(self.reasons)}
+        if self.err:
+            out["sampler_error"] = self.err
+        return out
 
 
 # ----------------------------------------------------------------------------- helpers

@@ -171,13 +171,11 @@ __device__ __forceinline__ void walk_face_parts(uint2 h, float px, float py, flo
                     __fmaf_rn(oy, __fsub_rn(fy, ray.oy), __fmul_rn(oz, __fsub_rn(fz, ray.oz))));
 }
 
-// Scene views the walk reads.  Two face layouts:
-//  * PaddedFaces: this library's own mirror. Rows start at padded_begin() (even
-//    slot => 16-byte aligned), so two faces arrive per 128-bit load; the
-//    neighbour index of a face sits at the same slot of `nbr`.  Unused slots
-//    hold zero faces (dp == 0 never wins).
-//  * CallerFaces: the caller's CSR + a caller-built half4[E] array (what
-//    trace_benchmark takes, pipeline.h:117-126); 64-bit loads.
+// Scene view the walk reads: this library's padded face mirror.  Rows start at
+// padded_begin() (a multiple of 4 slots => 32-byte aligned), so two faces arrive per 128-bit
+// load; the neighbour index of a face sits at the same slot of `nbr`.  Pad slots hold zero
+// faces (dp == 0 never wins).  trace_benchmark's caller-built half4[E] offsets
+// (pipeline.h:117-126) are copied into the same layout by build_faces_from_diff_kernel.
 struct PaddedFaces {
     const uint2 *faces;
     const uint32_t *nbr;
@@ -279,73 +277,6 @@ struct PaddedFaces {
     }
     __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {
         return __ldg(nbr + begin + face);
-    }
-};
-
-struct CallerFaces {
-    const uint2 *faces; // half4[E], caller CSR order
-    const uint32_t *adj;
-    const uint32_t *off;
-    __device__ __forceinline__ void row(uint32_t cell, uint32_t &begin, uint32_t &nf) const {
-        uint32_t a = __ldg(off + cell), b = __ldg(off + cell + 1);
-        begin = a;
-        nf = b - a;
-    }
-    // the reference's loop verbatim (exact IEEE quotient per face)
-    __device__ __forceinline__ void scan_exact(uint32_t begin, uint32_t nf, float px, float py,
-                                               float pz, const RayGeom &ray, float &t1,
-                                               uint32_t &face) const {
-        const uint2 *p = faces + begin;
-        for (uint32_t f = 0; f < nf; ++f) {
-            float t, dp;
-            walk_face(ldg2(p + f), px, py, pz, ray, t, dp);
-            if (dp > 0.0f && t < t1) { t1 = t; face = f; }
-        }
-    }
-    // ranked scan, same argument and same fallbacks as PaddedFaces::scan
-    __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
-                                         const RayGeom &ray, float &t1, uint32_t &face) const {
-        const float kInf = __int_as_float(0x7f800000);
-        const uint2 *p = faces + begin;
-        float best = kInf, second = kInf;
-        uint32_t bf = kNone;
-        bool any_front = false;
-        auto rank = [&](uint2 rec, uint32_t idx) {
-            float num, dp;
-            walk_face_parts(rec, px, py, pz, ray, num, dp);
-            float q = num * rcp_approx(dp);
-            bool front = dp > 0.0f;
-            any_front |= front;
-            q = front ? q : kInf;
-            bf = (q < best) ? idx : bf;
-            second = fminf(second, fmaxf(best, q));
-            best = fminf(best, q);
-        };
-        uint32_t f = 0;
-        for (; f + 2 <= nf; f += 2) {
-            uint2 a = ldg2(p + f);
-            uint2 b = ldg2(p + f + 1);
-            rank(a, f);
-            rank(b, f + 1);
-        }
-        if (f < nf)
-            rank(ldg2(p + f), f);
-        if (!any_front)
-            return; // unbounded hull cell: no face, t1 stays +inf
-        float ab = fabsf(best);
-        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
-        bool clear = (second - best) > margin;
-        if (clear && ab < 1e30f) {
-            float t, dp;
-            walk_face(ldg2(p + bf), px, py, pz, ray, t, dp);
-            t1 = t;
-            face = bf;
-        } else {
-            scan_exact(begin, nf, px, py, pz, ray, t1, face);
-        }
-    }
-    __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {
-        return __ldg(adj + begin + face);
     }
 };
 

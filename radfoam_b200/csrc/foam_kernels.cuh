@@ -14,20 +14,18 @@ __global__ void build_cells_kernel(const float *__restrict__ points,
                                    const AttrT *__restrict__ attrs, uint32_t num_points,
                                    int attr_dim_, int sh_row_, float4 *__restrict__ cells,
                                    float *__restrict__ sh_rows) {
-    // one thread per (point, slot) element of the SH mirror; slot 0 also writes the cell
-    uint64_t total = (uint64_t)num_points * (uint32_t)sh_row_;
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t i = (uint32_t)(idx / (uint32_t)sh_row_);
-        int s = (int)(idx - (uint64_t)i * (uint32_t)sh_row_);
+    // one warp per point row (grid-stride): lanes stream the row's SH coefficients, lane 0
+    // also writes the cell record -- no per-element 64-bit divisions, row-contiguous traffic
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < num_points; i += warps) {
         const AttrT *row = attrs + (uint64_t)i * attr_dim_;
-        float v = (s < attr_dim_ - 1) ? (float)row[s] : 0.0f;
-        sh_rows[idx] = v;
-        if (s == 0) {
-            float dens = (float)row[attr_dim_ - 1];
+        float *dst = sh_rows + (uint64_t)i * sh_row_;
+        for (int s = lane; s < sh_row_; s += 32)
+            dst[s] = (s < attr_dim_ - 1) ? (float)row[s] : 0.0f;
+        if (lane == 0)
             cells[i] = make_float4(points[3 * (uint64_t)i], points[3 * (uint64_t)i + 1],
-                                   points[3 * (uint64_t)i + 2], dens);
-        }
+                                   points[3 * (uint64_t)i + 2], (float)row[attr_dim_ - 1]);
     }
 }
 
@@ -58,6 +56,33 @@ __global__ void build_faces_kernel(const float *__restrict__ points, uint32_t nu
                 __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
                 rec.x = *reinterpret_cast<uint32_t *>(&hxy);
                 rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+            }
+            faces[dst + f] = rec;
+            nbr[dst + f] = j;
+        }
+    }
+}
+
+// Same padded layout, but the offsets are COPIED from a caller-built half4[E] array (what
+// trace_benchmark is given, pipeline.h:117-126) instead of derived from the points.
+__global__ void build_faces_from_diff_kernel(const uint2 *__restrict__ diff, uint32_t num_points,
+                                             const uint32_t *__restrict__ adj,
+                                             const uint32_t *__restrict__ off, uint2 *__restrict__ faces,
+                                             uint32_t *__restrict__ nbr) {
+    uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    uint32_t lane = threadIdx.x & 15;
+    uint32_t stride = (gridDim.x * blockDim.x) >> 4;
+    for (uint32_t i = group; i < num_points; i += stride) {
+        uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
+        uint32_t dst = padded_begin(a, i);
+        uint32_t nf = b - a, nf4 = (nf + 3u) & ~3u;
+        for (uint32_t f = lane; f < nf4; f += 16) {
+            uint2 rec = make_uint2(0u, 0u);
+            uint32_t j = 0;
+            if (f < nf) {
+                rec = ldg2(diff + a + f);
+                rec.y &= 0x0000FFFFu; // the 4th half is never read by the reference; keep it zero
+                j = __ldg(adj + a + f);
             }
             faces[dst + f] = rec;
             nbr[dst + f] = j;
@@ -721,23 +746,25 @@ template <typename AttrT>
 __global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t num_points,
                                       int attr_dim_, int sh_row_, float *__restrict__ points_grad,
                                       AttrT *__restrict__ attr_grad, int scrub) {
-    int gr = sh_row_ + 4;
-    uint64_t total = (uint64_t)num_points * (uint32_t)attr_dim_;
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t i = (uint32_t)(idx / (uint32_t)attr_dim_);
-        int s = (int)(idx - (uint64_t)i * (uint32_t)attr_dim_);
+    // one warp per accumulator row (grid-stride), row-contiguous reads and writes
+    const int gr = sh_row_ + 4;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < num_points; i += warps) {
         const float *row = acc + (uint64_t)i * gr;
-        float v = (s < attr_dim_ - 1) ? row[s] : row[sh_row_];
-        AttrT o = (AttrT)v;
-        if (scrub && !isfinite((float)o))
-            o = (AttrT)0.0f;
-        attr_grad[idx] = o;
-        if (s < 3) {
-            float gq = row[sh_row_ + 1 + s];
+        AttrT *out = attr_grad + (uint64_t)i * attr_dim_;
+        for (int s = lane; s < attr_dim_; s += 32) {
+            float v = (s < attr_dim_ - 1) ? row[s] : row[sh_row_];
+            AttrT o = (AttrT)v;
+            if (scrub && !isfinite((float)o))
+                o = (AttrT)0.0f;
+            out[s] = o;
+        }
+        if (lane < 3) {
+            float gq = row[sh_row_ + 1 + lane];
             if (scrub && !isfinite(gq))
                 gq = 0.0f;
-            points_grad[3 * (uint64_t)i + s] = gq;
+            points_grad[3 * (uint64_t)i + lane] = gq;
         }
     }
 }

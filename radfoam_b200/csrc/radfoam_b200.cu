@@ -67,12 +67,13 @@ struct DeviceBuffer {
 
 struct SceneKey {
     const void *points = nullptr, *attrs = nullptr, *adj = nullptr, *off = nullptr;
+    const void *diff = nullptr; // non-null: faces were copied from this caller-built array
     uint32_t n = 0, e = 0;
     uint64_t version = 0;
     bool faces = false;
     bool operator==(const SceneKey &o) const {
-        return points == o.points && attrs == o.attrs && adj == o.adj && off == o.off && n == o.n &&
-               e == o.e && version == o.version;
+        return points == o.points && attrs == o.attrs && adj == o.adj && off == o.off && diff == o.diff &&
+               n == o.n && e == o.e && version == o.version;
     }
 };
 
@@ -134,7 +135,7 @@ int check_device(rfb_pipeline *p) {
 // (Re)build the internal mirrors of the scene unless the caller vouches they are current.
 int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *attrs, uint32_t e,
                  const uint32_t *adj, const uint32_t *off, bool need_faces,
-                 const rfb_launch_opts *opts, cudaStream_t stream) {
+                 const rfb_launch_opts *opts, cudaStream_t stream, const void *caller_diff = nullptr) {
     if (int rc = check_device(p))
         return rc;
     SceneKey k;
@@ -142,6 +143,7 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     k.attrs = attrs;
     k.adj = adj;
     k.off = off;
+    k.diff = caller_diff;
     k.n = n;
     k.e = e;
     k.version = opts ? opts->scene_version : 0;
@@ -153,7 +155,7 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     RFB_CUDA(p->cells.ensure((size_t)n * sizeof(float4)));
     RFB_CUDA(p->sh_rows.ensure((size_t)n * SR * sizeof(float)));
     if (n) {
-        int grid = grid_for((uint64_t)n * SR, 256);
+        int grid = grid_for((uint64_t)n * 32, 256);
         if (p->attr_dtype == RFB_FLOAT16)
             build_cells_kernel<__half><<<grid, 256, 0, stream>>>(
                 points, reinterpret_cast<const __half *>(attrs), n, A, SR,
@@ -168,7 +170,12 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
         size_t slots = (size_t)padded_slots(n, e); // rows padded to 4 faces, <= 3 slack per row
         RFB_CUDA(p->faces.ensure(slots * sizeof(uint2)));
         RFB_CUDA(p->nbr.ensure(slots * sizeof(uint32_t)));
-        if (n) {
+        if (n && caller_diff) {
+            build_faces_from_diff_kernel<<<grid_for((uint64_t)n * 16, 256), 256, 0, stream>>>(
+                reinterpret_cast<const uint2 *>(caller_diff), n, adj, off,
+                reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
+            RFB_LAUNCHED();
+        } else if (n) {
             build_faces_kernel<<<grid_for((uint64_t)n * 16, 256), 256, 0, stream>>>(
                 points, n, adj, off, reinterpret_cast<uint2 *>(p->faces.ptr),
                 reinterpret_cast<uint32_t *>(p->nbr.ptr));
@@ -632,7 +639,7 @@ int rfb_trace_backward_finalize(rfb_pipeline *p, uint32_t num_points, float *poi
         return fail("rfb_trace_backward_finalize: no accumulated gradients for this point count");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
-    int grid = grid_for((uint64_t)num_points * A, 256);
+    int grid = grid_for((uint64_t)num_points * 32, 256);
     int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
     if (p->attr_dtype == RFB_FLOAT16)
         finalize_grads_kernel<__half><<<grid, 256, 0, stream>>>(
@@ -681,8 +688,28 @@ int rfb_trace_benchmark(rfb_pipeline *p, const rfb_trace_settings *settings, uin
     if (camera->width == 0 || camera->height == 0)
         return 0;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (int rc = ensure_scene(p, num_points, points, attributes, 0, point_adjacency,
-                              point_adjacency_offsets, false, opts, stream))
+    // The reference interface does not pass the adjacency size (pipeline.h:117-126); it is
+    // offsets[N].  Reading it costs a stream sync, paid only when the mirrors are (re)built.
+    uint32_t num_edges = p->key_valid ? p->key.e : 0;
+    {
+        SceneKey probe;
+        probe.points = points;
+        probe.attrs = attributes;
+        probe.adj = point_adjacency;
+        probe.off = point_adjacency_offsets;
+        probe.diff = adjacent_diff;
+        probe.n = num_points;
+        probe.e = num_edges;
+        probe.version = opts ? opts->scene_version : 0;
+        bool hit = p->key_valid && probe.version != 0 && probe == p->key && p->key.faces;
+        if (!hit) {
+            RFB_CUDA(cudaMemcpyAsync(&num_edges, point_adjacency_offsets + num_points, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, stream));
+            RFB_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+    if (int rc = ensure_scene(p, num_points, points, attributes, num_edges, point_adjacency,
+                              point_adjacency_offsets, true, opts, stream, adjacent_diff))
         return rc;
     rfb_trace_settings s = settings_or_default(settings);
     BenchmarkParams bp;
@@ -702,9 +729,10 @@ int rfb_trace_benchmark(rfb_pipeline *p, const rfb_trace_settings *settings, uin
     bp.max_steps = s.max_intersections;
     bp.blocks_x = (camera->width + 15) / 16;
     uint32_t blocks = bp.blocks_x * ((camera->height + 7) / 8);
-    CallerFaces fa;
-    fa.faces = reinterpret_cast<const uint2 *>(adjacent_diff);
-    fa.adj = point_adjacency;
+    // the caller's offsets, re-laid-out (copied, not recomputed) into the padded face rows
+    PaddedFaces fa;
+    fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
+    fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
     fa.off = point_adjacency_offsets;
     return launch_benchmark(p->sh_degree, bp, fa, blocks, stream);
 }
