@@ -126,6 +126,13 @@ int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points,
                                const uint32_t *point_adjacency_offsets,
                                void *adjacent_diff, void *stream);
 
+/* Entry cell of each query point = index of its nearest point (exact, brute force; ties -> lowest
+ * index).  Stands in for radfoam::nn over the AABB tree (src/aabb_tree/aabb_tree.h:18-27) for the
+ * one use the tracer has for it: the start cell of a camera (radfoam_model/scene.py:224-234).
+ * points[N][3], queries[M][3] f32, indices[M] u32, all device pointers. */
+int rfb_nearest_point(const float *points, uint32_t num_points, const float *queries,
+                      uint32_t num_queries, uint32_t *indices, void *stream);
+
 int rfb_trace_forward(rfb_pipeline *pipeline, const rfb_trace_settings *settings,
                       uint32_t num_points, const float *points,
                       const void *attributes, uint32_t point_adjacency_size,

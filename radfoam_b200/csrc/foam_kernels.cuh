@@ -240,7 +240,7 @@ struct Tape {
 // Forward with an explicit warp-synchronous loop (all lanes stay in the loop until the warp is
 // done, so lane 0 can allocate tape chunks for the warp) that records the tape.
 template <int DEG, typename Faces>
-__global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
+__global__ void __launch_bounds__(kBlock, 8) forward_record_kernel(const ForwardParams p, const Faces fa,
                                                                 const Tape tape) {
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -766,6 +766,57 @@ __global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t nu
                 gq = 0.0f;
             points_grad[3 * (uint64_t)i + lane] = gq;
         }
+    }
+}
+
+// ------------------------------------------------------------------ entry cell
+// Nearest point of each query = the Voronoi cell that contains it = the cell a ray from that
+// origin starts in (what scene.py:224-234 gets from radfoam.nn over the AABB tree,
+// aabb_tree.cu:343-415).  A camera origin is shared by every ray of a frame (and a training
+// batch has a few hundred distinct origins), so an exact brute-force scan -- one CTA per query,
+// 12 N bytes streamed, mostly from L2 -- is microseconds per query and needs no tree.
+// Ties (measure zero) resolve to the lowest index.  Distances in the x0 + (x1 + x2) order.
+__global__ void __launch_bounds__(256) nearest_point_kernel(const float *__restrict__ points,
+                                                            uint32_t num_points,
+                                                            const float *__restrict__ queries,
+                                                            uint32_t *__restrict__ out) {
+    const float qx = queries[3 * (uint64_t)blockIdx.x], qy = queries[3 * (uint64_t)blockIdx.x + 1],
+                qz = queries[3 * (uint64_t)blockIdx.x + 2];
+    float best = __int_as_float(0x7f800000);
+    uint32_t best_i = kNone;
+    for (uint32_t i = threadIdx.x; i < num_points; i += blockDim.x) {
+        float dx = points[3 * (uint64_t)i] - qx, dy = points[3 * (uint64_t)i + 1] - qy,
+              dz = points[3 * (uint64_t)i + 2] - qz;
+        float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+        if (d2 < best) { // strict: the lowest index among this thread's equals stays
+            best = d2;
+            best_i = i;
+        }
+    }
+    // (distance, index) lexicographic min over the CTA
+    __shared__ float s_d[8];
+    __shared__ uint32_t s_i[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_down_sync(0xffffffffu, best, o);
+        uint32_t oi = __shfl_down_sync(0xffffffffu, best_i, o);
+        if (od < best || (od == best && oi < best_i)) {
+            best = od;
+            best_i = oi;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_d[threadIdx.x >> 5] = best;
+        s_i[threadIdx.x >> 5] = best_i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (s_d[w] < best || (s_d[w] == best && s_i[w] < best_i)) {
+                best = s_d[w];
+                best_i = s_i[w];
+            }
+        out[blockIdx.x] = best_i;
     }
 }
 

@@ -465,6 +465,20 @@ int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points, uint32_
     return 0;
 }
 
+int rfb_nearest_point(const float *points, uint32_t num_points, const float *queries,
+                      uint32_t num_queries, uint32_t *indices, void *stream) {
+    if (num_queries == 0)
+        return 0;
+    if (!points || !queries || !indices)
+        return fail("rfb_nearest_point: NULL argument");
+    if (num_points == 0)
+        return fail("rfb_nearest_point: empty point set");
+    rfb::nearest_point_kernel<<<num_queries, 256, 0, (cudaStream_t)stream>>>(points, num_points, queries,
+                                                                              indices);
+    RFB_LAUNCHED();
+    return 0;
+}
+
 int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint32_t num_points,
                       const float *points, const void *attributes, uint32_t point_adjacency_size,
                       const uint32_t *point_adjacency, const uint32_t *point_adjacency_offsets,

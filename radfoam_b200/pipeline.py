@@ -499,6 +499,37 @@ def _wrap_device_memory(ptr: int, shape, device) -> torch.Tensor:
     return t.view(*shape)
 
 
+def nearest_point(points, queries):
+    """Entry cells: index of the nearest point of each query, ``uint32[M]`` (exact brute force on
+    the GPU; stands in for ``radfoam.nn(points, aabb_tree, queries)`` where the tracer needs it,
+    radfoam_model/scene.py:224-234, benchmark.py:88-89)."""
+    pts = points.detach().contiguous()
+    q = queries.detach().reshape(-1, 3).to(torch.float32).contiguous()
+    if pts.dtype != torch.float32 or pts.size(-1) != 3:
+        raise RuntimeError("points must be float32 [N, 3]")
+    if pts.device.type != "cuda" or q.device != pts.device:
+        raise RuntimeError("points and queries must be on the same CUDA device")
+    out = torch.empty((q.size(0),), dtype=torch.uint32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        stream = torch.cuda.current_stream(pts.device).cuda_stream
+        _lib.check(_lib.load().rfb_nearest_point(_ptr(pts), pts.size(0), _ptr(q), q.size(0), _ptr(out), stream))
+    return out
+
+
+def starting_points(rays, points):
+    """Start cell of every ray (mirror of RadFoamScene.get_starting_point, scene.py:224-234):
+    one nearest-point query per distinct ray origin, scattered back to the rays' batch shape."""
+    with torch.no_grad():
+        origins = rays[..., :3].reshape(-1, 3)
+        if origins.size(0) and bool((origins == origins[0]).all()):
+            # one camera (a rendered frame): a single query, broadcast
+            idx = nearest_point(points, origins[:1])
+            return idx.to(torch.int64).expand(origins.size(0)).to(torch.uint32).reshape(rays.shape[:-1])
+        unique, inverse = torch.unique(origins, dim=0, return_inverse=True)
+        idx = nearest_point(points, unique).to(torch.int64)
+        return idx[inverse].to(torch.uint32).reshape(rays.shape[:-1])
+
+
 def create_pipeline(sh_degree, attr_dtype="float32") -> Pipeline:
     """radfoam.create_pipeline (pipeline_bindings.cpp:587-590, 669-672)."""
     if not isinstance(sh_degree, int) or sh_degree < 0 or sh_degree > 3:

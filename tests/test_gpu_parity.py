@@ -363,6 +363,33 @@ def test_tape_is_not_replayed_for_other_rays(torch_cuda):
     assert common.grad_error(a["points_grad"].cpu().numpy(), b["points_grad"].cpu().numpy()) < 1e-5
 
 
+# ------------------------------------------------------------------ entry cell
+def test_nearest_point_and_starting_points(torch_cuda):
+    import radfoam_b200
+    from radfoam_b200 import foam
+
+    torch = torch_cuda
+    f = common.scene_case(num_points=60000, width=320, height=200).foam
+    rng = np.random.default_rng(2)
+    queries = np.concatenate([rng.normal(0, 2.0, size=(257, 3)), f.points[:5].astype(np.float64)]).astype(np.float32)
+    got = radfoam_b200.nearest_point(to_dev(torch, f.points), to_dev(torch, queries)).cpu().numpy()
+    d2 = ((f.points[None, :, :].astype(np.float64) - queries[:, None, :].astype(np.float64)) ** 2).sum(-1)
+    want = d2.argmin(axis=1)
+    # exact up to fp32-vs-fp64 near-ties: the chosen point must be (numerically) as close as the best
+    chosen = d2[np.arange(len(queries)), got.astype(np.int64)]
+    assert (chosen <= d2.min(axis=1) * (1 + 1e-5) + 1e-12).all()
+    assert (got.astype(np.int64) == want).mean() > 0.99
+    assert np.array_equal(got[-5:], np.arange(5))        # a point is its own nearest point
+    # per-ray start cells: one frame (single origin) and a multi-camera batch
+    case = common.scene_case(num_points=60000, width=320, height=200)
+    sp = radfoam_b200.starting_points(to_dev(torch, case.rays), to_dev(torch, f.points))
+    assert sp.dtype == torch.uint32 and sp.shape == case.start.shape
+    assert np.array_equal(sp.cpu().numpy(), case.start)
+    batch = common.random_ray_case(num_points=60000, num_rays=100000)
+    sp = radfoam_b200.starting_points(to_dev(torch, batch.rays), to_dev(torch, batch.foam.points))
+    assert np.array_equal(sp.cpu().numpy(), batch.start)
+
+
 # ------------------------------------------------------------------ invariants
 def test_tiled_and_linear_assignment_agree(torch_cuda):
     case = common.scene_case()
