@@ -129,6 +129,35 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- helpers
+class InputPrefetcher:
+    """Host -> device feed for the e2e legs of BOTH arms: step i's inputs are copied from pinned
+    host memory on a private copy stream into one of two pre-allocated device buffer sets, one
+    step ahead of their use -- what the reference's BatchFetcher does
+    (src/utils/batch_fetcher.cpp:44-117: cuMemcpyHtoDAsync on its own stream, ring of batches)."""
+
+    def __init__(self, host, keys, dev):
+        import torch
+
+        self.torch, self.host, self.keys, self.dev = torch, host, keys, dev
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [{k: torch.empty_like(host[k], device=dev) for k in keys} for _ in range(2)]
+        self.free = [None, None]  # event: the compute that last read this buffer set has finished
+
+    def enqueue(self, i):
+        torch = self.torch
+        b = i % 2
+        with torch.cuda.stream(self.stream):
+            if self.free[b] is not None:
+                self.stream.wait_event(self.free[b])
+            for k in self.keys:
+                self.bufs[b][k].copy_(self.host[k], non_blocking=True)
+            ev = self.stream.record_event()
+        return self.bufs[b], ev
+
+    def release(self, i):
+        self.free[i % 2] = self.torch.cuda.current_stream(self.dev).record_event()
+
+
 def measured_peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -267,18 +296,7 @@ def run_ours(args):
     pts_p = points.detach().clone().requires_grad_(True)
     attrs_p = attrs.detach().clone().requires_grad_(True)
 
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def h2d_async():
-        """Enqueue this step's inputs host -> device on the copy stream (like the reference's
-        BatchFetcher, src/utils/batch_fetcher.cpp:44-117: async H2D on a private stream)."""
-        main = torch.cuda.current_stream(dev)
-        with torch.cuda.stream(copy_stream):
-            batch = {k: shard_host[k].to(dev, non_blocking=True) for k in ("rays", "start", "dq", "target")}
-            for t in batch.values():
-                t.record_stream(main)
-            ev = copy_stream.record_event()
-        return batch, ev
+    fetch = InputPrefetcher(shard_host, ("rays", "start", "dq", "target"), dev)
 
     def step_e2e(batch, ev):
         torch.cuda.current_stream(dev).wait_event(ev)
@@ -296,13 +314,14 @@ def run_ours(args):
     def run_e2e(steps):
         """K steps; every step's H2D copy is issued inside this region, one step ahead of its use
         (copy of step i+1 overlaps the kernels of step i); the loss is read back every step."""
-        nxt = h2d_async()
+        nxt = fetch.enqueue(0)
         last = 0.0
         for i in range(steps):
             batch, ev = nxt
             if i + 1 < steps:
-                nxt = h2d_async()
+                nxt = fetch.enqueue(i + 1)
             last = float(step_e2e(batch, ev).item())  # D2H read of the step's result
+            fetch.release(i)
         return last
 
     # --- warm-up (also gives the work counters)
@@ -504,17 +523,28 @@ def run_reference(args):
 
     pts_p, attrs_p = points.clone().requires_grad_(True), attrs.clone().requires_grad_(True)
 
-    def step_e2e():
-        rays = host["rays"].to(dev, non_blocking=True)
-        start = host["start"].to(dev, non_blocking=True)
-        dq = host["dq"].to(dev, non_blocking=True)
-        target = host["target"].to(dev, non_blocking=True)
+    fetch = InputPrefetcher(host, ("rays", "start", "dq", "target"), dev)
+
+    def step_e2e(batch, ev):
+        torch.cuda.current_stream(dev).wait_event(ev)
         pts_p.grad = None
         attrs_p.grad = None
-        rgba, depth = RefTraceRays.apply(pts_p, attrs_p, rays, start, dq)
-        loss = ((rgba - target) ** 2).sum() / R + 1e-4 * (depth[..., 0] - depth[..., 1]).abs().sum() / R
+        rgba, depth = RefTraceRays.apply(pts_p, attrs_p, batch["rays"], batch["start"], batch["dq"])
+        loss = (((rgba - batch["target"]) ** 2).sum() / R
+                + 1e-4 * (depth[..., 0] - depth[..., 1]).abs().sum() / R)
         loss.backward()
-        return float(loss.item())
+        return loss
+
+    def run_e2e(steps):
+        nxt = fetch.enqueue(0)
+        last = 0.0
+        for i in range(steps):
+            batch, ev = nxt
+            if i + 1 < steps:
+                nxt = fetch.enqueue(i + 1)
+            last = float(step_e2e(batch, ev).item())
+            fetch.release(i)
+        return last
 
     for _ in range(max(args.warmup, 3)):
         fwd, _ = step_device()
@@ -530,13 +560,11 @@ def run_reference(args):
     torch.cuda.synchronize()
     ms_per_step = ev0.elapsed_time(ev1) / args.steps
     clocks = sampler.stop()
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        loss_val = step_e2e()
+    loss_val = run_e2e(args.steps)
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / args.steps

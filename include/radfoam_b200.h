@@ -193,7 +193,7 @@ int rfb_trace_benchmark(rfb_pipeline *pipeline, const rfb_trace_settings *settin
                         const uint32_t *start_point_index, uint32_t *output_rgba,
                         const rfb_launch_opts *opts, void *stream);
 
-/* kernels launched by this library on the calling thread since the last reset
+/* kernels launched by this library (all threads of the process) since the last reset
  * (bench.py reports it as gpu_launches) */
 uint64_t rfb_launch_count(void);
 void rfb_reset_launch_count(void);

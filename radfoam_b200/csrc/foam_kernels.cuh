@@ -240,7 +240,7 @@ struct Tape {
 // Forward with an explicit warp-synchronous loop (all lanes stay in the loop until the warp is
 // done, so lane 0 can allocate tape chunks for the warp) that records the tape.
 template <int DEG, typename Faces>
-__global__ void __launch_bounds__(kBlock, 8) forward_record_kernel(const ForwardParams p, const Faces fa,
+__global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
                                                                 const Tape tape) {
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;

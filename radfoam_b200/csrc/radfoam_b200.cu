@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <string>
@@ -16,7 +17,7 @@
 namespace {
 
 thread_local std::string g_last_error;
-thread_local uint64_t g_launches = 0;
+std::atomic<uint64_t> g_launches{0}; // process-wide: autograd runs backward on its own thread
 
 int fail(const std::string &msg) {
     g_last_error = msg;
@@ -370,8 +371,8 @@ extern "C" {
 
 const char *rfb_last_error(void) { return g_last_error.c_str(); }
 int rfb_abi_version(void) { return RFB_ABI_VERSION; }
-uint64_t rfb_launch_count(void) { return g_launches; }
-void rfb_reset_launch_count(void) { g_launches = 0; }
+uint64_t rfb_launch_count(void) { return g_launches.load(); }
+void rfb_reset_launch_count(void) { g_launches.store(0); }
 
 int rfb_create_pipeline(int sh_degree, int attr_dtype, rfb_pipeline **out) {
     if (!out)
