@@ -149,10 +149,20 @@ class InputPrefetcher:
         with torch.cuda.stream(self.stream):
             if self.free[b] is not None:
                 self.stream.wait_event(self.free[b])
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(self.stream)
             for k in self.keys:
                 self.bufs[b][k].copy_(self.host[k], non_blocking=True)
-            ev = self.stream.record_event()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(self.stream)
+        self.last = (t0, ev)
         return self.bufs[b], ev
+
+    def last_copy_ms(self):
+        """Duration of the most recent H2D batch on the copy stream (diagnostic: PCIe health)."""
+        t0, t1 = self.last
+        t1.synchronize()
+        return float(t0.elapsed_time(t1))
 
     def release(self, i):
         self.free[i % 2] = self.torch.cuda.current_stream(self.dev).record_event()
@@ -370,6 +380,7 @@ def run_ours(args):
     barrier(world)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
     h2d = sum(shard_host[k].numel() * shard_host[k].element_size() for k in ("rays", "start", "dq", "target"))
+    h2d_ms = fetch.last_copy_ms()
 
     if rank != 0:
         return
@@ -408,7 +419,8 @@ def run_ours(args):
                    "l2": "scene working set (417 MB) larger than L2 (126 MB); no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": R_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "loss": loss_val},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "loss": loss_val,
+                "h2d_ms_per_step": h2d_ms, "h2d_overlapped": True},
         "gpu_launches": int(launches),
         "kernels_ms": {"forward_kernel": k_fwd, "backward_kernel": k_bwd},
         "walk_tape": tape,
@@ -569,6 +581,7 @@ def run_reference(args):
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / args.steps
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("rays", "start", "dq", "target"))
+    h2d_ms = fetch.last_copy_ms()
     value = R / (ms_per_step * 1e-3) / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
@@ -584,7 +597,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference",
                          "sample": "full frame; GPU kernels of the reference, one host launch thread"},
         "e2e": {"value": R / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "loss": loss_val},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "loss": loss_val,
+                "h2d_ms_per_step": h2d_ms, "h2d_overlapped": True},
     }
     print(json.dumps(line), flush=True)
 
