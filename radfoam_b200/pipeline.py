@@ -61,6 +61,12 @@ class Pipeline:
         # backward of the same step replays it instead of re-scanning faces
         self.record_tape = True
         self._tape_refs = None
+        # unordered ray batches ([R, 6], the reference's training batches: train.py:61) are traced
+        # in a coherent order -- sorted by (start cell, direction) -- and the per-ray outputs are
+        # scattered back; results are unchanged, neighbouring lanes share cells again
+        self.reorder_rays = True
+        self.reorder_min_rays = 1 << 15
+        self._reorder = None
 
     def __del__(self):
         try:
@@ -151,6 +157,46 @@ class Pipeline:
         if start_point.device.type != "cuda":
             raise RuntimeError("start_point must be on CUDA device")
 
+    @staticmethod
+    def _coherent_order(rays_c, start_c):
+        """Permutation sorting rays by (start cell, Morton code of the direction on the octahedral
+        map): rays of one camera with neighbouring directions become neighbours in the batch."""
+        dirs = torch.nn.functional.normalize(rays_c[:, 3:6], dim=1)
+        o = dirs[:, :2] / dirs.abs().sum(dim=1, keepdim=True).clamp_min(1e-30)
+        o = torch.where(dirs[:, 2:3] < 0, (1 - o.flip(1).abs()) * torch.where(o < 0, -1.0, 1.0), o)
+        uv = ((o * 0.5 + 0.5).clamp(0, 1) * 1023).to(torch.int64)
+
+        def spread(v):
+            v = (v | (v << 8)) & 0x00FF00FF
+            v = (v | (v << 4)) & 0x0F0F0F0F
+            v = (v | (v << 2)) & 0x33333333
+            return (v | (v << 1)) & 0x55555555
+
+        key = (start_c.to(torch.int64) << 20) | spread(uv[:, 0]) | (spread(uv[:, 1]) << 1)
+        return torch.argsort(key)
+
+    @staticmethod
+    def _take(t, perm):
+        """t[perm] along dim 0, also for uint32 tensors (indexing is not implemented for them)."""
+        if t is None:
+            return None
+        if t.dtype == torch.uint32:
+            return t.view(torch.int32)[perm].view(torch.uint32)
+        return t[perm]
+
+    @staticmethod
+    def _untake(t_sorted, perm):
+        """Inverse of _take: out[perm] = t_sorted."""
+        if t_sorted is None:
+            return None
+        if t_sorted.dtype == torch.uint32:
+            out = torch.empty_like(t_sorted).view(torch.int32)
+            out[perm] = t_sorted.view(torch.int32)
+            return out.view(torch.uint32)
+        out = torch.empty_like(t_sorted)
+        out[perm] = t_sorted
+        return out
+
     def _tape_flag(self, rays_c, start_c, scene_version) -> int:
         """FLAG_USE_TAPE iff these are the very tensors (unmodified) of the last recording forward."""
         refs = self._tape_refs
@@ -212,6 +258,15 @@ class Pipeline:
 
         settings = self._settings(weight_threshold, max_intersections)
         dev = rays_c.device
+        perm = None
+        self._reorder = None
+        if self.reorder_rays and rays_c.dim() == 2 and num_rays >= self.reorder_min_rays:
+            with torch.no_grad():
+                perm = self._coherent_order(rays_c, start_c)
+                sorted_in = (self._take(rays_c, perm), self._take(start_c, perm), self._take(dq_c, perm))
+            self._reorder = ((weakref.ref(rays_c), rays_c._version), (weakref.ref(start_c), start_c._version),
+                             perm, sorted_in)
+            rays_c, start_c, dq_c = sorted_in
         batch = list(rays_c.shape[:-1])
         rgba = torch.empty(batch + [4], dtype=self._dtype, device=dev)
         num_intersections = torch.empty(batch + [1], dtype=torch.uint32, device=dev)
@@ -237,6 +292,9 @@ class Pipeline:
                 num_q, _ptr(dq_c), _ptr(rgba), _ptr(depth), _ptr(depth_indices),
                 _ptr(num_intersections), _ptr(contribution), ctypes.byref(opts), stream))
 
+        if perm is not None:  # back to the caller's ray order
+            rgba, num_intersections = self._untake(rgba, perm), self._untake(num_intersections, perm)
+            depth, depth_indices = self._untake(depth, perm), self._untake(depth_indices, perm)
         out = {"rgba": rgba}
         if return_depth:
             out["depth"] = depth
@@ -245,6 +303,20 @@ class Pipeline:
             out["contribution"] = contribution
         out["num_intersections"] = num_intersections
         return out
+
+    def _sorted_backward_args(self, rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c):
+        """If the last forward traced these very rays in a coherent order, hand the backward the
+        same sorted tensors (so that the walk tape matches) and permute its per-ray inputs."""
+        ro = self._reorder
+        if ro is None:
+            return rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c
+        (r_ref, r_ver), (s_ref, s_ver), perm, (rays_k, start_k, dq_k) = ro
+        if not (r_ref() is rays_c and r_ver == rays_c._version and s_ref() is start_c
+                and s_ver == start_c._version):
+            return rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c
+        take = self._take
+        return (rays_k, start_k, take(rgb_c, perm), take(grad_c, perm), dq_k if dq_c is not None else None,
+                take(di_c, perm), take(dg_c, perm), take(err_c, perm))
 
     def _backward_args(self, points, attributes, point_adjacency, point_adjacency_offsets, rays,
                        start_point, rgb_out, grad_in, depth_quantiles, depth_indices,
@@ -334,6 +406,9 @@ class Pipeline:
          err_c, num_rays, num_q) = self._backward_args(
             points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out,
             grad_in, depth_quantiles, depth_indices, depth_grad_in, ray_error)
+        with torch.no_grad():
+            rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c = self._sorted_backward_args(
+                rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c)
         num_points = points_c.size(0)
         dev = rays_c.device
         settings = self._settings(weight_threshold, max_intersections)
@@ -374,6 +449,9 @@ class Pipeline:
          err_c, num_rays, num_q) = self._backward_args(
             points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out,
             grad_in, depth_quantiles, depth_indices, depth_grad_in, ray_error)
+        with torch.no_grad():
+            rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c = self._sorted_backward_args(
+                rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c)
         num_points = points_c.size(0)
         dev = rays_c.device
         settings = self._settings(weight_threshold, max_intersections)
