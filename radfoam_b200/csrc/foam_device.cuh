@@ -337,6 +337,29 @@ __device__ __forceinline__ void isect_grad(float px, float py, float pz, float q
     gz = __fdiv_rn(__fmaf_rn(num, ray.dz, __fmul_rn(dp, __fsub_rn(ray.oz, pz))), inv);
 }
 
+// Both directions of one bisector at once: gp = d t / d p and gq = d t / d q for the plane
+// between p and q.  Swapping the roles of p and q negates n, dp and num exactly (negation
+// commutes with rounding) and leaves a and dp*dp unchanged, so the second gradient reuses them:
+//   gq_i = -( fma(num, d_i, dp * (o_i - q_i)) / (dp*dp) )
+// bit-identical to isect_grad(q, p, ...), at roughly half its cost.
+__device__ __forceinline__ void isect_grad_pair(float px, float py, float pz, float qx, float qy,
+                                                float qz, const RayGeom &ray, float &gpx, float &gpy,
+                                                float &gpz, float &gqx, float &gqy, float &gqz) {
+    float nx = __fsub_rn(qx, px), ny = __fsub_rn(qy, py), nz = __fsub_rn(qz, pz);
+    float ax = __fmaf_rn(__fadd_rn(px, qx), 0.5f, -ray.ox);
+    float ay = __fmaf_rn(__fadd_rn(py, qy), 0.5f, -ray.oy);
+    float az = __fmaf_rn(__fadd_rn(pz, qz), 0.5f, -ray.oz);
+    float dp = __fmaf_rn(nx, ray.dx, __fmaf_rn(ny, ray.dy, __fmul_rn(nz, ray.dz)));
+    float num = __fmaf_rn(nx, ax, __fmaf_rn(ny, ay, __fmul_rn(nz, az)));
+    float inv = __fmul_rn(dp, dp);
+    gpx = __fdiv_rn(__fmaf_rn(num, ray.dx, __fmul_rn(dp, __fsub_rn(ray.ox, px))), inv);
+    gpy = __fdiv_rn(__fmaf_rn(num, ray.dy, __fmul_rn(dp, __fsub_rn(ray.oy, py))), inv);
+    gpz = __fdiv_rn(__fmaf_rn(num, ray.dz, __fmul_rn(dp, __fsub_rn(ray.oz, pz))), inv);
+    gqx = -__fdiv_rn(__fmaf_rn(num, ray.dx, __fmul_rn(dp, __fsub_rn(ray.ox, qx))), inv);
+    gqy = -__fdiv_rn(__fmaf_rn(num, ray.dy, __fmul_rn(dp, __fsub_rn(ray.oy, qy))), inv);
+    gqz = -__fdiv_rn(__fmaf_rn(num, ray.dz, __fmul_rn(dp, __fsub_rn(ray.oz, qz))), inv);
+}
+
 // Per-ray state of the backward pass and the analytic gradients of one composited cell
 // (backward cell functor, pipeline.cu:219-331; SURVEY.md Appendix A.4/A.5, quirks kept).
 // Shared by both backward kernels; every multiply-add is pinned to the reference's SASS
@@ -416,13 +439,14 @@ struct BackwardRay {
         const float dL_dt1 = dL_dd;
 
         // position gradients through t0 / t1 (pipeline.cu:284-313)
-        float ax = 0.0f, ay = 0.0f, az = 0.0f;
-        if (prev != kNone)
-            isect_grad(ppx, ppy, ppz, pc.x, pc.y, pc.z, ray, ax, ay, az); // dt0/dprev
-        float bx, by, bz, ex, ey, ez, nx, ny, nz;
-        isect_grad(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz); // dt1/dcur
-        isect_grad(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez);    // dt0/dcur
-        isect_grad(pn.x, pn.y, pn.z, pc.x, pc.y, pc.z, ray, nx, ny, nz); // dt1/dnext
+        float ax, ay, az, bx, by, bz, ex, ey, ez, nx, ny, nz;
+        // entry plane (prev | cur): e = dt0/dcur, a = dt0/dprev; exit plane (cur | next):
+        // b = dt1/dcur, n = dt1/dnext.  Before the first composited cell prev_point is the
+        // origin (quirk A.5.2) and dt0/dprev is defined as zero (pipeline.cu:284-289).
+        isect_grad_pair(pc.x, pc.y, pc.z, ppx, ppy, ppz, ray, ex, ey, ez, ax, ay, az);
+        if (prev == kNone)
+            ax = ay = az = 0.0f;
+        isect_grad_pair(pc.x, pc.y, pc.z, pn.x, pn.y, pn.z, ray, bx, by, bz, nx, ny, nz);
         pgx = __fmaf_rn(dL_dt0, ax, pgx);
         pgy = __fmaf_rn(dL_dt0, ay, pgy);
         pgz = __fmaf_rn(dL_dt0, az, pgz);
