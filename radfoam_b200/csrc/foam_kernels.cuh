@@ -303,9 +303,9 @@ __global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardPar
                 if (face == kNone) {
                     done = true;
                 } else {
-                    if (chunk != kTapeNoChunk)
-                        tape.pool[((uint64_t)chunk * kTapeChunk + (k % kTapeChunk)) * 32 + lane] =
-                            make_uint2(cur, __float_as_uint(t1));
+                    if (chunk != kTapeNoChunk) // streaming store: the tape is written once, read once
+                        __stcs(tape.pool + ((uint64_t)chunk * kTapeChunk + (k % kTapeChunk)) * 32 + lane,
+                               make_uint2(cur, __float_as_uint(t1)));
                     nrec++;
                     uint32_t nxt = fa.neighbour(begin, face);
                     float4 pn = ldg4(p.cells + nxt);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 
     extern __shared__ __align__(16) float smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int WARP_FLOATS = 32 * GR + SLOTS * GR + SLOTS;
+    constexpr int WARP_FLOATS = (32 * GR + SLOTS * GR + SLOTS + 3) & ~3; // keeps every warp's rows 16-byte aligned
     float *stage = smem + warp * WARP_FLOATS;                          // [32][GR]
     float *cache = stage + 32 * GR;                                    // [SLOTS][GR]
     uint32_t *tags = reinterpret_cast<uint32_t *>(cache + SLOTS * GR); // [SLOTS]
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     uint2 recB = make_uint2(0u, 0u);
     auto tape_row = [&](uint32_t chunk_id, uint32_t j) -> uint2 {
         // record j of this lane; past the end: the cell the forward stopped in
-        return j < nrec ? tape.pool[((uint64_t)chunk_id * kTapeChunk + (j % kTapeChunk)) * 32 + lane]
+        return j < nrec ? __ldcs(tape.pool + ((uint64_t)chunk_id * kTapeChunk + (j % kTapeChunk)) * 32 + lane)
                         : make_uint2(last_cell, 0u);
     };
     if (replay) {

@@ -291,7 +291,7 @@ template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS, boo
 int launch_backward_cached_one(const BackwardParams &bp, const Faces &fa, const Tape &tape,
                                uint32_t blocks, cudaStream_t stream) {
     constexpr int GR = grad_row(DEG);
-    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * GR + SLOTS * GR + SLOTS) * sizeof(float);
+    constexpr size_t smem = (size_t)(kBlock / 32) * ((32 * GR + SLOTS * GR + SLOTS + 3) & ~3) * sizeof(float);
     auto kernel = backward_cached_kernel<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS, REPLAY>;
     static bool configured = false; // per instantiation; the attribute is idempotent
     if (!configured) {
@@ -319,16 +319,20 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const 
 template <int DEG, typename Faces>
 int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, const Tape &tape,
                                uint32_t blocks, cudaStream_t stream) {
-    // Shipped configuration: 8 cache slots per warp, groups of >= 8 lanes go through the
-    // cache, 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200),
-    // re-walk backward: direct 29.3 ms; (32 slots, >=2, 4 CTAs) 21.5; (16, >=4, 5) 17.7;
-    // (16, >=8, 5) 16.6; (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower
-    // (profiles/r01_backward_variants.json).  RFB_BWD_VARIANT selects neighbours for re-tuning.
+    // Shipped configuration: 4 cache slots per warp, groups of >= 6 lanes go through the cache,
+    // 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200):
+    //   re-walk backward: direct 29.3 ms; (32 slots, >=2 lanes, 4 CTAs) 21.5; (16, >=4, 5) 17.7;
+    //                     (16, >=8, 5) 16.6; (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower;
+    //   replay backward:  (8, >=8, 5) 11.2; (4, >=8) 11.2; (2, >=8) 11.2; (4, >=4) 10.8;
+    //                     (4, >=5) 10.5; (2, >=6) 10.5; (4, >=6) 10.46  <- shipped
+    // (profiles/r01_backward_variants*.json).  With 4 slots the CTA's shared memory drops below
+    // 32 KB, so 5 CTAs fit the 164 KB carve-out and the SM keeps 92 KB of L1 instead of 60.
+    // RFB_BWD_VARIANT selects neighbours for re-tuning on other scenes.
     switch (variant) {
-    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 4, 5>(bp, fa, tape, blocks, stream);
-    case 2: return launch_backward_cached_cfg<DEG, Faces, 8, 12, 5>(bp, fa, tape, blocks, stream);
-    case 3: return launch_backward_cached_cfg<DEG, Faces, 16, 8, 5>(bp, fa, tape, blocks, stream);
-    default: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, tape, blocks, stream);
+    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, tape, blocks, stream);
+    case 2: return launch_backward_cached_cfg<DEG, Faces, 4, 5, 5>(bp, fa, tape, blocks, stream);
+    case 3: return launch_backward_cached_cfg<DEG, Faces, 2, 6, 5>(bp, fa, tape, blocks, stream);
+    default: return launch_backward_cached_cfg<DEG, Faces, 4, 6, 5>(bp, fa, tape, blocks, stream);
     }
 }
 

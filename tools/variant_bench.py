@@ -37,6 +37,7 @@ os.environ["RFB_BWD_MODE"] = "cached"
 os.environ["RFB_BWD_VARIANT"] = "0"
 out = bwd()
 res["rewalk_v0_ms"] = timeit(bwd)
+print("rewalk", res["rewalk_v0_ms"], flush=True)
 # walk tape: recording forward + replaying backward
 scene[0].requires_grad_(True)
 pipe.record_tape = True
@@ -49,6 +50,7 @@ for v in range(4):
     out = bwd()
     res[f"replay_v{v}_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
     res[f"replay_v{v}_ms"] = timeit(bwd)
+    print(v, res[f"replay_v{v}_ms"], flush=True)
 print(json.dumps(res, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/variant_bench.json", "w"), indent=1)
