@@ -11,7 +11,8 @@ import pytest
 import common
 from oracle import oracle
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("benchmark"))
 
 
 def test_golden_vectors_present():
@@ -55,3 +56,28 @@ def test_golden_inputs_are_the_seeded_cases():
     assert np.array_equal(z["adjacency"], case.foam.adjacency)
     assert np.array_equal(z["rays"], case.rays)
     assert np.array_equal(z["grad_rgba"], case.grad_rgba)
+
+
+BENCH = os.path.join(os.path.dirname(__file__), "golden", "benchmark2k.npz")
+
+
+@pytest.mark.parametrize("tag", ["f16", "f32"])
+@pytest.mark.parametrize("model", ["pinhole", "fisheye"])
+def test_oracle_trace_benchmark_reproduces_reference_frames(tag, model):
+    """trace_benchmark (in-kernel cast_ray + RGBA8 packing, benchmark.py's FPS path): the CPU
+    restatement vs frames the reference's own benchmark<> kernel rendered on a B200
+    (tests/golden/make_golden_benchmark.py).  RGBA8 truncates v*255, so an expf-level difference
+    may move a channel by one LSB on a few pixels; nothing larger is allowed."""
+    z = dict(np.load(BENCH))
+    cam = {k: z[f"cam_{model}_{k}"] for k in ("position", "forward", "right", "up")}
+    cam.update(fov=float(z[f"cam_{model}_fov"]), width=64, height=48, model=model)
+    # the offsets the reference was given (its own prefetch) equal the restatement's
+    diff = oracle.prefetch_adjacent_diff(z["points"], z["adjacency"], z["offsets"])
+    assert np.array_equal(diff.view(np.uint16), z["adjacent_diff"].view(np.uint16))
+    img = oracle.trace_benchmark(z["points"], z["attributes_" + tag], z["adjacency"], z["offsets"], diff, cam,
+                                 int(z[f"start_{model}"][0]), weight_threshold=0.05)
+    a = img.view(np.uint8).reshape(48, 64, 4).astype(np.int32)
+    b = z[f"image_{tag}_{model}"].view(np.uint8).reshape(48, 64, 4).astype(np.int32)
+    assert (b[..., :3].sum(axis=-1) > 0).mean() > 0.2      # the golden frame is not empty
+    assert np.abs(a - b).max() <= 1
+    assert (a != b).any(axis=-1).mean() < 5e-3
