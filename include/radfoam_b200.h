@@ -133,6 +133,17 @@ int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points,
 int rfb_nearest_point(const float *points, uint32_t num_points, const float *queries,
                       uint32_t num_queries, uint32_t *indices, void *stream);
 
+/* Per point i: indices[i] = the adjacent point farthest from it (first maximum in row order; UINT32_MAX when
+ * the row is empty or every neighbour coincides with it), cell_radius[i] = sum(0.5*|p_j - p_i|) / num_faces
+ * (NaN for an empty row).  Replaces radfoam::farthest_neighbor (src/delaunay/triangulation_ops.h:8-15, kernel
+ * triangulation_ops.cu:9-44; pybind farthest_neighbor, torch_bindings/triangulation_bindings.cpp:184-216), the
+ * CSR pass the densification step runs before sampling new points (radfoam_model/scene.py:434-461).
+ * Bit-identical outputs.  points[N][3] f32, CSR as for the tracer, indices[N] u32, cell_radius[N] f32. */
+int rfb_farthest_neighbor(const float *points, uint32_t num_points,
+                          const uint32_t *point_adjacency,
+                          const uint32_t *point_adjacency_offsets,
+                          uint32_t *indices, float *cell_radius, void *stream);
+
 int rfb_trace_forward(rfb_pipeline *pipeline, const rfb_trace_settings *settings,
                       uint32_t num_points, const float *points,
                       const void *attributes, uint32_t point_adjacency_size,

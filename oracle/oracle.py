@@ -44,6 +44,8 @@ def load():
                                             P, c_float, c_uint32, c_uint32, c_int, c_uint32, P, c_int]
         lib.rfo_trace_benchmark.restype = c_int
         lib.rfo_max_threads.restype = c_int
+        lib.rfo_farthest_neighbor.argtypes = [P, c_uint32, P, P, P, P]
+        lib.rfo_farthest_neighbor.restype = None
         _lib = lib
     return _lib
 
@@ -77,6 +79,18 @@ def prefetch_adjacent_diff(points, adjacency, offsets):
     out = np.zeros((adjacency.shape[0], 4), dtype=np.float16)
     load().rfo_prefetch_adjacent_diff(_p(points), points.shape[0], _p(adjacency), _p(offsets), _p(out))
     return out
+
+
+def farthest_neighbor(points, adjacency, offsets):
+    """(indices uint32[N], cell_radius float32[N]); triangulation_ops.cu:9-44."""
+    points = _c(points, np.float32)
+    adjacency = _c(adjacency, np.uint32)
+    offsets = _c(offsets, np.uint32)
+    n = points.shape[0]
+    indices = np.zeros((n,), dtype=np.uint32)
+    radius = np.zeros((n,), dtype=np.float32)
+    load().rfo_farthest_neighbor(_p(points), n, _p(adjacency), _p(offsets), _p(indices), _p(radius))
+    return indices, radius
 
 
 def trace_forward(points, attributes, adjacency, offsets, rays, start_point, depth_quantiles=None,

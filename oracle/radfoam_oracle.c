@@ -630,6 +630,34 @@ int rfo_trace_benchmark(int sh_degree, int attr_is_half, float weight_threshold,
     return 0;
 }
 
+/* farthest_neighbor_kernel, src/delaunay/triangulation_ops.cu:9-44.
+ * Row order, strict '>' against a running maximum that starts at 0 (so a neighbour at distance 0 or NaN never
+ * wins and an empty row leaves UINT32_MAX); `sum_distance += 0.5 * distance` is a DOUBLE add rounded back to
+ * float every iteration; radius = sum / (float)num_faces (0/0 = NaN for an empty row).  |q - p| as the SASS
+ * has it: sqrt(fma(dx,dx, fma(dy,dy, dz*dz))), IEEE sqrt. */
+void rfo_farthest_neighbor(const float *points, uint32_t num_points, const uint32_t *adj,
+                           const uint32_t *off, uint32_t *indices, float *cell_radius) {
+    for (uint32_t i = 0; i < num_points; ++i) {
+        const float *p = points + 3 * (size_t)i;
+        const uint32_t begin = off[i], num_faces = off[i + 1] - begin;
+        uint32_t farthest_idx = RF_NONE;
+        float sum_distance = 0.0f, max_distance = 0.0f;
+        for (uint32_t f = 0; f < num_faces; ++f) {
+            const uint32_t j = adj[begin + f];
+            const float *q = points + 3 * (size_t)j;
+            const float dx = q[0] - p[0], dy = q[1] - p[1], dz = q[2] - p[2];
+            const float distance = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            sum_distance = (float)((double)sum_distance + 0.5 * (double)distance);
+            if (distance > max_distance) {
+                max_distance = distance;
+                farthest_idx = j;
+            }
+        }
+        indices[i] = farthest_idx;
+        cell_radius[i] = sum_distance / (float)num_faces;
+    }
+}
+
 int rfo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

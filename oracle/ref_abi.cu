@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "delaunay/triangulation_ops.h"
 #include "tracing/pipeline.h"
 #include "utils/cuda_array.h"
 
@@ -122,6 +123,17 @@ int rfref_prefetch_adjacent_diff(const float *points, uint32_t num_points,
             reinterpret_cast<const radfoam::Vec3f *>(points), num_points,
             point_adjacency_size, point_adjacency, point_adjacency_offsets,
             reinterpret_cast<radfoam::Vec4h *>(adjacent_diff), nullptr);
+    });
+}
+
+// radfoam::farthest_neighbor, src/delaunay/triangulation_ops.h:8-15 (its TU, triangulation_ops.cu, is the
+// second reference source compiled into this library, also unmodified)
+int rfref_farthest_neighbor(const float *points, uint32_t num_points, const uint32_t *point_adjacency,
+                            const uint32_t *point_adjacency_offsets, uint32_t *indices,
+                            float *cell_radius) {
+    return guarded([&] {
+        radfoam::farthest_neighbor(radfoam::Float32, points, point_adjacency,
+                                   point_adjacency_offsets, num_points, indices, cell_radius, nullptr);
     });
 }
 

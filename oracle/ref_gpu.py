@@ -40,6 +40,7 @@ def load():
                                               P, P, P, P, c_float, c_uint32, c_uint32, c_int, P, P]
         lib.rfref_prefetch_adjacent_diff.argtypes = [P, c_uint32, c_uint32, P, P, P]
         lib.rfref_release_pool.restype = None
+        lib.rfref_farthest_neighbor.argtypes = [P, c_uint32, P, P, P, P]
         _lib = lib
     return _lib
 
@@ -119,6 +120,16 @@ def prefetch_adjacent_diff(points, adjacency, offsets):
     _check(load().rfref_prefetch_adjacent_diff(_ptr(points), points.size(0), adjacency.numel(),
                                                _ptr(adjacency), _ptr(offsets), _ptr(out)))
     return out
+
+
+def farthest_neighbor(points, adjacency, offsets):
+    """The reference's own kernel (triangulation_ops.cu:9-44) -> (indices uint32[N], cell_radius f32[N])."""
+    n = points.size(0)
+    indices = torch.zeros((n,), dtype=torch.uint32, device=points.device)
+    radius = torch.zeros((n,), dtype=torch.float32, device=points.device)
+    _check(load().rfref_farthest_neighbor(_ptr(points), n, _ptr(adjacency), _ptr(offsets), _ptr(indices),
+                                          _ptr(radius)))
+    return indices, radius
 
 
 def trace_benchmark(points, attributes, adjacency, offsets, adjacent_diff, camera, start_point,

@@ -14,11 +14,11 @@ no CPU fallback).
 from . import foam  # noqa: F401  (numpy/scipy only)
 
 __all__ = ["create_pipeline", "Pipeline", "TraceRays", "ShardedTracer", "nearest_point", "starting_points",
-           "foam", "library_path"]
+           "farthest_neighbor", "foam", "library_path"]
 
 
 def __getattr__(name):
-    if name in ("create_pipeline", "Pipeline", "nearest_point", "starting_points"):
+    if name in ("create_pipeline", "Pipeline", "nearest_point", "starting_points", "farthest_neighbor"):
         from . import pipeline as _p
         return getattr(_p, name)
     if name == "TraceRays":

@@ -47,6 +47,7 @@ SIGNATURES = {
     "rfb_attribute_type": (c_int, [_P]),
     "rfb_prefetch_adjacent_diff": (c_int, [_P, c_uint32, c_uint32, _P, _P, _P, _P]),
     "rfb_nearest_point": (c_int, [_P, c_uint32, _P, c_uint32, _P, _P]),
+    "rfb_farthest_neighbor": (c_int, [_P, c_uint32, _P, _P, _P, _P, _P]),
     "rfb_trace_forward": (c_int, [_P, POINTER(TraceSettings), c_uint32, _P, _P, c_uint32, _P, _P,
                                   c_uint32, _P, _P, c_uint32, _P, _P, _P, _P, _P, _P,
                                   POINTER(LaunchOpts), _P]),

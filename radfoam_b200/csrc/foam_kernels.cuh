@@ -820,6 +820,118 @@ __global__ void __launch_bounds__(256) nearest_point_kernel(const float *__restr
     }
 }
 
+// ------------------------------------------------------------------ farthest neighbour
+// Per cell: the adjacent point farthest from it and half the mean neighbour distance ("cell radius"),
+// what the densification pass reads (scene.py:434-461; reference kernel triangulation_ops.cu:9-44, one
+// thread per point walking its row with dependent gathers of three scalar loads each).
+// Arithmetic as the reference's SASS has it: d = q - p, |d|^2 = fma(dx,dx, fma(dy,dy, dz*dz)), IEEE sqrt and
+// divide, strict '>' first-max from 0, and `sum += 0.5 * dist` evaluated in fp64 and rounded back to fp32 every
+// iteration.  That last step needs no fp64: 0.5*dist is exact and rounding an exact sum to 53 then to 24 bits
+// equals rounding it to 24 bits directly whenever 53 >= 2*24 + 2 (double rounding is innocuous for +), so
+// fmaf(dist, 0.5f, sum) is bit-identical; the FP64CHAIN variants keep the literal form.
+constexpr uint32_t kRowLanes = 8;
+
+struct PackedPoints { // the caller's [N][3] array: three scalar loads per point
+    const float *p;
+    __device__ __forceinline__ float3 operator[](uint64_t i) const {
+        return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+    }
+};
+struct PaddedPoints { // a float4 mirror: one 16-byte load per point
+    const float4 *p;
+    __device__ __forceinline__ float3 operator[](uint64_t i) const {
+        const float4 v = __ldg(p + i);
+        return make_float3(v.x, v.y, v.z);
+    }
+};
+
+__global__ void __launch_bounds__(256) pad_points_kernel(const float *__restrict__ points, uint32_t num_points,
+                                                         float4 *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num_points)
+        out[i] = make_float4(points[3 * i], points[3 * i + 1], points[3 * i + 2], 0.0f);
+}
+
+__device__ __forceinline__ float neighbour_distance(float3 q, float3 p) {
+    const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y), dz = __fsub_rn(q.z, p.z);
+    return __fsqrt_rn(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))));
+}
+
+template <bool FP64CHAIN>
+__device__ __forceinline__ float half_distance_sum(float sum, float dist) {
+    if (FP64CHAIN)
+        return __double2float_rn(__fma_rn((double)dist, 0.5, (double)sum));
+    return __fmaf_rn(dist, 0.5f, sum);
+}
+
+// 8 lanes share a row: the adjacency read is one 32-byte sector and the 8 neighbour gathers are in flight
+// together; the reference's in-order accumulation is then replayed over the 8 distances by shuffle.
+template <typename Points, bool FP64CHAIN>
+__global__ void __launch_bounds__(256) farthest_neighbor_kernel(Points points,
+                                                                const uint32_t *__restrict__ adjacency,
+                                                                const uint32_t *__restrict__ offsets,
+                                                                uint32_t num_points,
+                                                                uint32_t *__restrict__ indices,
+                                                                float *__restrict__ cell_radius) {
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & (kRowLanes - 1u);
+    const uint32_t group_mask = 0xffu << (lane & ~(kRowLanes - 1u));
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes;
+    if (i >= num_points) // the 8 lanes of a row leave together
+        return;
+    const float3 p = points[i];
+    const uint32_t begin = offsets[i], num_faces = offsets[i + 1] - begin;
+    float sum = 0.0f, farthest = 0.0f;
+    uint32_t farthest_face = kNone;
+    for (uint32_t f0 = 0; f0 < num_faces; f0 += kRowLanes) {
+        const uint32_t f = f0 + sub;
+        float dist = 0.0f;
+        if (f < num_faces)
+            dist = neighbour_distance(points[adjacency[begin + f]], p);
+        const uint32_t count = min(kRowLanes, num_faces - f0);
+        for (uint32_t k = 0; k < count; ++k) { // every lane of the row replays the same sequence
+            const float dk = __shfl_sync(group_mask, dist, k, kRowLanes);
+            sum = half_distance_sum<FP64CHAIN>(sum, dk);
+            if (dk > farthest) {
+                farthest = dk;
+                farthest_face = f0 + k;
+            }
+        }
+    }
+    if (sub == 0) {
+        indices[i] = farthest_face == kNone ? kNone : adjacency[begin + farthest_face];
+        cell_radius[i] = __fdiv_rn(sum, __uint2float_rn(num_faces)); // 0/0 = NaN for an empty row, as upstream
+    }
+}
+
+// One thread per row (the reference's shape), for comparison: fewer instructions per face, scattered reads.
+template <typename Points, bool FP64CHAIN>
+__global__ void __launch_bounds__(256) farthest_neighbor_rows_kernel(Points points,
+                                                                     const uint32_t *__restrict__ adjacency,
+                                                                     const uint32_t *__restrict__ offsets,
+                                                                     uint32_t num_points,
+                                                                     uint32_t *__restrict__ indices,
+                                                                     float *__restrict__ cell_radius) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_points)
+        return;
+    const float3 p = points[i];
+    const uint32_t begin = offsets[i], num_faces = offsets[i + 1] - begin;
+    float sum = 0.0f, farthest = 0.0f;
+    uint32_t farthest_idx = kNone;
+#pragma unroll 4
+    for (uint32_t f = 0; f < num_faces; ++f) {
+        const uint32_t j = adjacency[begin + f];
+        const float dist = neighbour_distance(points[j], p);
+        sum = half_distance_sum<FP64CHAIN>(sum, dist);
+        if (dist > farthest) {
+            farthest = dist;
+            farthest_idx = j;
+        }
+    }
+    indices[i] = farthest_idx;
+    cell_radius[i] = __fdiv_rn(sum, __uint2float_rn(num_faces));
+}
+
 // ------------------------------------------------------------------ benchmark
 struct CameraParams {
     float position[3], forward[3], right[3], up[3];

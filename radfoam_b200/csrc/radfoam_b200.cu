@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <atomic>
 #include <cstring>
 #include <new>
@@ -481,6 +482,71 @@ int rfb_nearest_point(const float *points, uint32_t num_points, const float *que
     rfb::nearest_point_kernel<<<num_queries, 256, 0, (cudaStream_t)stream>>>(points, num_points, queries,
                                                                               indices);
     RFB_LAUNCHED();
+    return 0;
+}
+
+int rfb_farthest_neighbor(const float *points, uint32_t num_points, const uint32_t *point_adjacency,
+                          const uint32_t *point_adjacency_offsets, uint32_t *indices, float *cell_radius,
+                          void *stream_) {
+    if (num_points == 0)
+        return 0;
+    if (!points || !point_adjacency_offsets || !indices || !cell_radius)
+        return fail("rfb_farthest_neighbor: NULL argument");
+    // point_adjacency may be NULL only when every row is empty; the kernels never read it then
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // Variants, all verified bit-identical to the reference's kernel on a B200 (profiles/r01_farthest_neighbor.json);
+    // RFB_FARTHEST_VARIANT picks one for measurement (tools/farthest_bench.py):
+    //   3  8 lanes per row, caller's [N][3] points, fp32 fma accumulation           (default: fastest measured)
+    //   0  the same with the literal fp64 accumulation (F2F/DFMA bound: 0.164 vs 0.128 ms at 1M points)
+    //   1  8 lanes per row, float4 point mirror, fp32 fma accumulation
+    //   2  one thread per row, float4 point mirror, fp32 fma accumulation
+    //   4  one thread per row, caller's points, fp32 fma accumulation (the reference's shape)
+    const char *env = getenv("RFB_FARTHEST_VARIANT");
+    const int variant = env ? atoi(env) : 3;
+    const uint32_t row_grid = (uint32_t)(((uint64_t)num_points + 255) / 256);
+    const uint32_t lane_grid = (uint32_t)(((uint64_t)num_points * rfb::kRowLanes + 255) / 256);
+    const rfb::PackedPoints packed{points};
+    if (variant == 1 || variant == 2) {
+        // stream-ordered scratch; keep freed blocks in the pool (the default threshold of 0 returns them to the
+        // driver at the next synchronisation: 2 ms per call measured)
+        static std::once_flag pool_once;
+        std::call_once(pool_once, [] {
+            int dev = 0;
+            cudaMemPool_t pool = nullptr;
+            uint64_t keep = ~0ull;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaGetLastError();
+        });
+        float4 *mirror = nullptr;
+        if (cudaMallocAsync(&mirror, sizeof(float4) * (size_t)num_points, stream) != cudaSuccess) {
+            cudaGetLastError();
+            return fail("rfb_farthest_neighbor: out of device memory for the point mirror");
+        }
+        rfb::pad_points_kernel<<<row_grid, 256, 0, stream>>>(points, num_points, mirror);
+        RFB_LAUNCHED();
+        const rfb::PaddedPoints padded{mirror};
+        if (variant == 1)
+            rfb::farthest_neighbor_kernel<rfb::PaddedPoints, false><<<lane_grid, 256, 0, stream>>>(
+                padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        else
+            rfb::farthest_neighbor_rows_kernel<rfb::PaddedPoints, false><<<row_grid, 256, 0, stream>>>(
+                padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCHED();
+        cudaFreeAsync(mirror, stream);
+    } else if (variant == 0) {
+        rfb::farthest_neighbor_kernel<rfb::PackedPoints, true><<<lane_grid, 256, 0, stream>>>(
+            packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCHED();
+    } else if (variant == 4) {
+        rfb::farthest_neighbor_rows_kernel<rfb::PackedPoints, false><<<row_grid, 256, 0, stream>>>(
+            packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCHED();
+    } else {
+        rfb::farthest_neighbor_kernel<rfb::PackedPoints, false><<<lane_grid, 256, 0, stream>>>(
+            packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCHED();
+    }
     return 0;
 }
 

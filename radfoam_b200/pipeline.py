@@ -608,6 +608,37 @@ def starting_points(rays, points):
         return idx[inverse].to(torch.uint32).reshape(rays.shape[:-1])
 
 
+def farthest_neighbor(points, point_adjacency, point_adjacency_offsets):
+    """``radfoam.farthest_neighbor`` (torch_bindings/triangulation_bindings.cpp:184-216): returns
+    ``(indices uint32[N], cell_radius float32[N])`` -- per point, the adjacent point farthest from it and half
+    the mean neighbour distance; what ``prune_and_densify`` reads (radfoam_model/scene.py:434-461)."""
+    if points.device.type != "cuda":
+        raise RuntimeError("points must be on CUDA device")
+    pts = points.detach().contiguous()
+    if pts.dtype != torch.float32:
+        raise RuntimeError("unsupported scalar type")  # triangulation_ops.cu:83-85
+    if pts.dim() < 2 or pts.size(-1) != 3:
+        raise RuntimeError("points must have shape [N, 3]")
+    adj = point_adjacency.detach().contiguous()
+    off = point_adjacency_offsets.detach().contiguous()
+    for name, t in (("point_adjacency", adj), ("point_adjacency_offsets", off)):
+        if t.dtype != torch.uint32:
+            raise RuntimeError(f"{name} must have uint32 dtype")
+        if t.device != pts.device:
+            raise RuntimeError(f"{name} must be on the same device as points")
+    num_points = pts.size(0)
+    if off.numel() != num_points + 1:
+        raise RuntimeError("point_adjacency_offsets must have num_points + 1 elements")
+    shape = tuple(pts.shape[:-1])
+    indices = torch.empty(shape, dtype=torch.uint32, device=pts.device)
+    cell_radius = torch.empty(shape, dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        stream = torch.cuda.current_stream(pts.device).cuda_stream
+        _lib.check(_lib.load().rfb_farthest_neighbor(_ptr(pts), num_points, _ptr(adj), _ptr(off), _ptr(indices),
+                                                     _ptr(cell_radius), stream))
+    return indices, cell_radius
+
+
 def create_pipeline(sh_degree, attr_dtype="float32") -> Pipeline:
     """radfoam.create_pipeline (pipeline_bindings.cpp:587-590, 669-672)."""
     if not isinstance(sh_degree, int) or sh_degree < 0 or sh_degree > 3:

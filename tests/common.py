@@ -129,3 +129,74 @@ def assert_forward_close_cpu(got: dict, ref: dict, attributes: np.ndarray) -> No
         # a float scatter-add like the gradients: norm-scaled
         assert grad_error(got["contribution"].astype(np.float32),
                           ref["contribution"].astype(np.float32)) <= 1e-5
+
+
+def farthest_edge_case():
+    """A hand-built CSR (not a triangulation) for farthest_neighbor's corner cases: an empty row, a row whose
+    neighbours all coincide with the point, an exact tie (first wins), rows of 9 / 21 / 40 faces (more than one
+    8-lane pass), overflowing / underflowing / NaN coordinates, and rows mixing magnitudes 1e-12..1e12 so that the
+    fp64-add-then-round-to-fp32 accumulation is exercised."""
+    from radfoam_b200 import foam
+
+    rng = np.random.default_rng(77)
+    n = 96
+    pts = rng.uniform(-1.0, 1.0, size=(n, 3)).astype(np.float32)
+    pts[1] = pts[2] = pts[3] = pts[0]                     # row 0: all neighbours coincide
+    pts[4] = np.float32([0.25, 0.5, -0.75])
+    pts[5] = pts[4] + np.float32([0.5, 0.0, 0.0])         # row 4: exact tie between 5 and 6
+    pts[6] = pts[4] - np.float32([0.5, 0.0, 0.0])
+    pts[7] = pts[4] + np.float32([0.25, 0.0, 0.0])
+    pts[8] = np.float32([3e19, 0.0, 0.0])                 # |d|^2 overflows -> inf
+    pts[9] = np.float32([1e-30, 1e-30, 0.0])              # |d|^2 underflows
+    pts[10] = np.float32([0.0, 0.0, 0.0])
+    pts[11] = np.float32([np.nan, 0.0, 0.0])
+    scale = np.float32(10.0) ** rng.integers(-12, 13, size=(n - 40, 1)).astype(np.float32)
+    pts[40:] *= scale
+    rows = [[] for _ in range(n)]
+    rows[0] = [1, 2, 3]
+    rows[4] = [7, 5, 6]
+    rows[8] = [10, 12, 13]
+    rows[10] = [9, 9]
+    rows[12] = [8, 11, 13]                                 # inf and NaN distances in one row
+    rows[11] = [10, 12]                                    # every distance NaN
+    rows[13] = []                                          # empty row -> UINT32_MAX, NaN
+    for i, k in ((14, 8), (15, 9), (16, 21), (17, 40), (18, 1), (19, 16), (20, 17)):
+        rows[i] = list(rng.choice(np.arange(20, 40), size=k, replace=k > 20))
+    for i in range(40, n):
+        rows[i] = list(rng.choice(np.arange(40, n), size=int(rng.integers(3, 30)), replace=False))
+    off = np.zeros(n + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    adj = np.array([j for r in rows for j in r], dtype=np.uint32)
+    return foam.Foam(pts, np.zeros((n, 4), dtype=np.float32), adj, off, 0)
+
+
+def farthest_neighbor_numpy(points, adjacency, offsets):
+    """Independent restatement of triangulation_ops.cu:9-44 in numpy scalars (slow; small cases only)."""
+    n = points.shape[0]
+    idx = np.full(n, NONE, dtype=np.uint32)
+    radius = np.zeros(n, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        for i in range(n):
+            p = points[i]
+            s, m = np.float32(0.0), np.float32(0.0)
+            b, e = int(offsets[i]), int(offsets[i + 1])
+            for f in range(b, e):
+                d = points[adjacency[f]] - p
+                # fma(dx,dx, fma(dy,dy, dz*dz)) with a single rounding per fma: exact in float64 then rounded
+                inner = np.float32(np.float64(d[1]) * np.float64(d[1]) + np.float64(np.float32(d[2] * d[2])))
+                sq = np.float32(np.float64(d[0]) * np.float64(d[0]) + np.float64(inner))
+                dist = np.sqrt(sq, dtype=np.float32)
+                s = np.float32(np.float64(s) + 0.5 * np.float64(dist))
+                if dist > m:
+                    m, idx[i] = dist, adjacency[f]
+            radius[i] = s / np.float32(e - b) if e > b else np.float32(np.nan)
+    return idx, radius
+
+
+def assert_same_floats(got: np.ndarray, ref: np.ndarray) -> None:
+    """Bit-for-bit equality of two float32 arrays, any NaN matching any NaN (payloads differ between libm/GPU)."""
+    got, ref = np.asarray(got, dtype=np.float32), np.asarray(ref, dtype=np.float32)
+    assert got.shape == ref.shape
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got[~nan].view(np.uint32), ref[~nan].view(np.uint32))

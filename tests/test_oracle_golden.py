@@ -12,7 +12,7 @@ import common
 from oracle import oracle
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("benchmark"))
+                if not os.path.basename(p).startswith(("benchmark", "farthest")))
 
 
 def test_golden_vectors_present():
