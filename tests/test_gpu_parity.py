@@ -498,3 +498,59 @@ def test_validation_errors(torch_cuda):
         pipe.trace_forward(pts.cpu(), attrs, adj, off, rays, start)
     with pytest.raises(RuntimeError, match="rays must have 6"):
         pipe.trace_forward(pts, attrs, adj, off, rays[..., :5], start)
+
+
+# ------------------------------------------------------------------ .pt checkpoint -> FPS loop
+def test_pt_checkpoint_benchmark_loop(torch_cuda, tmp_path):
+    """A scene saved in the reference's .pt layout, loaded as benchmark.py:36-38 does (fp16 attributes), rendered
+    through the FPS loop of benchmark.py:86-139; frames must equal direct trace_benchmark calls and, when
+    oracle/_ref is built, the reference kernel's frames (<= 1 level on a few pixels, as test_trace_benchmark)."""
+    import radfoam_b200
+    from oracle import ref_gpu
+    from radfoam_b200 import foam, scene_io
+
+    torch = torch_cuda
+    f = common.scene_case().foam
+    path = tmp_path / "model.pt"
+    scene_io.FoamScene.from_foam(f, device="cpu").save_pt(path)
+    scene = scene_io.FoamScene.load_pt(path, sh_degree=3, attr_dtype=torch.float16, device="cuda")
+    width, height, fov = 160, 96, 0.9
+    c2w = torch.zeros((17, 4, 4))
+    dicts = []
+    for i in range(17):
+        ang = 0.37 * i
+        pos = (3.2 * np.cos(ang), 3.2 * np.sin(ang), 1.5)
+        cam = foam.camera_dict(pos, fov=fov, width=width, height=height)
+        dicts.append(cam)
+        c2w[i, :3, 0] = torch.from_numpy(cam["right"])
+        c2w[i, :3, 1] = -torch.from_numpy(cam["up"])
+        c2w[i, :3, 2] = torch.from_numpy(cam["forward"])
+        c2w[i, :3, 3] = torch.from_numpy(cam["position"])
+        c2w[i, 3, 3] = 1.0
+    fy = height / (2.0 * np.tan(fov / 2.0))
+    cameras, positions = scene_io.benchmark_cameras(c2w, fy, width, height)
+    assert len(cameras) == 3 and abs(cameras[0]["fov"] - fov) < 1e-6
+    pipe = radfoam_b200.create_pipeline(3, "float16")
+    res = scene_io.benchmark_fps(pipe, scene, cameras, positions, n_reps=2)
+    assert res["frames"] == 3 and res["fps"] > 0 and res["output"].shape == (3, height, width)
+    frames = res["output"].cpu().numpy()
+    points, attributes, adjacency, offsets = scene.get_trace_data()
+    assert attributes.dtype == torch.float16
+    diff = pipe.prefetch_adjacent_diff(points, adjacency, offsets)
+    starts = radfoam_b200.nearest_point(points, positions.cuda())
+    for k, pose in enumerate((0, 8, 16)):
+        start = starts[k:k + 1].clone()
+        direct = torch.zeros((height, width), dtype=torch.uint32, device="cuda")
+        pipe.trace_benchmark(points, attributes, adjacency, offsets, diff, cameras[k], start, direct,
+                             weight_threshold=0.05)
+        assert np.array_equal(frames[k], direct.cpu().numpy())
+        a = frames[k].view(np.uint8).reshape(height, width, 4).astype(np.int32)
+        assert (a[..., :3].sum(axis=-1) > 0).mean() > 0.2          # the frame is not empty
+        if ref_gpu.available():
+            ref_out = torch.zeros((height, width), dtype=torch.uint32, device="cuda")
+            cam_np = {key: (v.numpy() if isinstance(v, torch.Tensor) else v) for key, v in cameras[k].items()}
+            ref_gpu.trace_benchmark(points, attributes, adjacency, offsets, diff, cam_np, start, ref_out,
+                                    weight_threshold=0.05)
+            torch.cuda.synchronize()
+            b = ref_out.cpu().numpy().view(np.uint8).reshape(height, width, 4).astype(np.int32)
+            assert np.abs(a - b).max() <= 1 and (a != b).any(axis=-1).mean() < 2e-3
