@@ -495,7 +495,7 @@ int rfb_farthest_neighbor(const float *points, uint32_t num_points, const uint32
     // point_adjacency may be NULL only when every row is empty; the kernels never read it then
     cudaStream_t stream = (cudaStream_t)stream_;
     // Variants, all verified bit-identical to the reference's kernel on a B200 (profiles/r01_farthest_neighbor.json);
-    // RFB_FARTHEST_VARIANT picks one for measurement (tools/farthest_bench.py):
+    // RFB_FARTHEST_VARIANT picks one for measurement (tests/tools/farthest_bench.py):
     //   3  8 lanes per row, caller's [N][3] points, fp32 fma accumulation           (default: fastest measured)
     //   0  the same with the literal fp64 accumulation (F2F/DFMA bound: 0.164 vs 0.128 ms at 1M points)
     //   1  8 lanes per row, float4 point mirror, fp32 fma accumulation

@@ -75,6 +75,20 @@ def test_product_never_imports_the_oracle():
                 assert "radfoam_oracle" not in text and "libradfoam_ref" not in text, f
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """Outside tests/ and oracle/ itself, only bench.py (cpu_baseline / --impl reference legs) and
+    __graft_entry__.py (build + smoke's check) may mention the oracle."""
+    allowed = {"bench.py", "__graft_entry__.py"}
+    for dirpath, dirs, files in os.walk(ROOT):
+        rel = os.path.relpath(dirpath, ROOT)
+        dirs[:] = [d for d in dirs if not d.startswith(".") and d not in ("gpurun_out", "__pycache__")
+                   and os.path.join(rel, d) not in ("./tests", "./oracle", "./baseline")]
+        for f in files:
+            if f.endswith(".py") and os.path.join(rel, f).lstrip("./") not in allowed:
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(rel, f)
+
+
 def test_pipeline_methods_take_the_reference_binding_arguments():
     """Argument names / order / defaults of the pybind11 Pipeline the reference's Python code calls
     (torch_bindings/pipeline_bindings.cpp:626-672), so radfoam_model/render.py:33-42, 80-93 and

@@ -1,8 +1,8 @@
 """FPS of a radfoam ``.pt`` checkpoint through this library -- the reference's benchmark.py:95-139 loop on
 ``radfoam_b200`` (fp16 attributes, weight_threshold 0.05, in-kernel ray generation, RGBA8 frames).
 
-    python tools/benchmark_scene.py path/to/model.pt [--sh-degree 3] [--width 1920 --height 1080]
-    python tools/benchmark_scene.py --synthetic 1048576          # no checkpoint: a synthetic foam saved to .pt first
+    python tests/tools/benchmark_scene.py path/to/model.pt [--sh-degree 3] [--width 1920 --height 1080]
+    python tests/tools/benchmark_scene.py --synthetic 1048576          # no checkpoint: a synthetic foam saved to .pt first
 
 Real checkpoints carry their test cameras in the dataset, which is out of scope here; the poses are an orbit around the
 scene's centre at 2.5x its RMS radius, every 8th of 64 used as in benchmark.py:63-64."""
@@ -15,7 +15,7 @@ import tempfile
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import radfoam_b200  # noqa: E402
 from radfoam_b200 import foam, scene_io  # noqa: E402

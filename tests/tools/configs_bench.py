@@ -1,5 +1,5 @@
 """BASELINE.json configs 2, 3, 5 on one GPU: parity vs the reference's kernels + timings.
-python tools/configs_bench.py [2 3 5]"""
+python tests/tools/configs_bench.py [2 3 5]"""
 import json
 import os
 import sys
@@ -8,14 +8,14 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import common  # noqa: E402
 import radfoam_b200  # noqa: E402
 from oracle import ref_gpu  # noqa: E402
 from radfoam_b200 import foam  # noqa: E402
-from tools.quick_bench import timeit  # noqa: E402
+from quick_bench import timeit  # noqa: E402
 
 CONFIGS = {
     2: dict(points=524_288, width=1920, height=1080, q=0, backward=False, pos=(0.3, 0.3, 0.3), target=(1.0, 0.2, -0.1)),

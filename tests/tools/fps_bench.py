@@ -7,13 +7,13 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import radfoam_b200  # noqa: E402
 from oracle import ref_gpu  # noqa: E402
 from radfoam_b200 import foam  # noqa: E402
-from tools.quick_bench import timeit  # noqa: E402
+from quick_bench import timeit  # noqa: E402
 
 points = int(sys.argv[1]) if len(sys.argv) > 1 else 1_048_576
 f = bench.load_or_build_foam(points, print)

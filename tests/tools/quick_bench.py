@@ -1,5 +1,5 @@
 """Ad-hoc timing of ours vs the reference's own kernels on one GPU (not bench.py):
-python tools/quick_bench.py --points 1000000 --width 1920 --height 1080"""
+python tests/tools/quick_bench.py --points 1000000 --width 1920 --height 1080"""
 import argparse
 import json
 import os
@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import common  # noqa: E402

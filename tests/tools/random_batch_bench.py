@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
@@ -16,7 +16,7 @@ import common  # noqa: E402
 import radfoam_b200  # noqa: E402
 from oracle import ref_gpu  # noqa: E402
 from radfoam_b200 import foam  # noqa: E402
-from tools.quick_bench import timeit  # noqa: E402
+from quick_bench import timeit  # noqa: E402
 
 f = bench.load_or_build_foam(1_048_576, print)
 rng = np.random.default_rng(64)

@@ -1,5 +1,5 @@
 """Turn an .ncu-rep (brought back in gpurun_out/) into the compact summary kept under profiles/.
-usage: python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_name.md"""
+usage: python tests/tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_name.md"""
 import csv
 import io
 import subprocess
