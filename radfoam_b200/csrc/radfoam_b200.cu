@@ -294,10 +294,14 @@ int launch_backward_cached_one(const BackwardParams &bp, const Faces &fa, const 
     constexpr int GR = grad_row(DEG);
     constexpr size_t smem = (size_t)(kBlock / 32) * ((32 * GR + SLOTS * GR + SLOTS + 3) & ~3) * sizeof(float);
     auto kernel = backward_cached_kernel<DEG, Faces, SLOTS, MIN_GROUP, MIN_BLOCKS, REPLAY>;
-    static bool configured = false; // per instantiation; the attribute is idempotent
-    if (!configured) {
+    // the attribute is per device and idempotent: set it once per (instantiation, device)
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    RFB_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
         RFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.fetch_or(bit, std::memory_order_relaxed);
     }
     kernel<<<blocks, kBlock, smem, stream>>>(bp, fa, tape);
     RFB_LAUNCHED();
@@ -524,7 +528,6 @@ int rfb_farthest_neighbor(const float *points, uint32_t num_points, const uint32
             return fail("rfb_farthest_neighbor: out of device memory for the point mirror");
         }
         rfb::pad_points_kernel<<<row_grid, 256, 0, stream>>>(points, num_points, mirror);
-        RFB_LAUNCHED();
         const rfb::PaddedPoints padded{mirror};
         if (variant == 1)
             rfb::farthest_neighbor_kernel<rfb::PaddedPoints, false><<<lane_grid, 256, 0, stream>>>(
@@ -532,8 +535,10 @@ int rfb_farthest_neighbor(const float *points, uint32_t num_points, const uint32
         else
             rfb::farthest_neighbor_rows_kernel<rfb::PaddedPoints, false><<<row_grid, 256, 0, stream>>>(
                 padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
-        RFB_LAUNCHED();
-        cudaFreeAsync(mirror, stream);
+        g_launches += 2;
+        const cudaError_t launched = cudaGetLastError();
+        cudaFreeAsync(mirror, stream); // stream-ordered: after the kernels above, also on the error path
+        RFB_CUDA(launched);
     } else if (variant == 0) {
         rfb::farthest_neighbor_kernel<rfb::PackedPoints, true><<<lane_grid, 256, 0, stream>>>(
             packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
