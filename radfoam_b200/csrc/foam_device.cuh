@@ -46,9 +46,13 @@ __device__ __forceinline__ uint2 ldg2(const uint2 *p) { return __ldg(p); }
 // 16-byte fire-and-forget reduction (sm_90+): one L2 atomic transaction for four
 // consecutive floats instead of four scalar REDs.
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+#ifdef RFB_EMU // tests/emu: kernel-logic emulation on the CPU (test infrastructure)
+    rfb_emu_red_add_v4(addr, a, b, c, d);
+#else
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
                  "f"(c), "f"(d)
                  : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------- SH basis
@@ -151,10 +155,14 @@ __device__ __forceinline__ void walk_face(uint2 h, float px, float py, float pz,
 // MUFU.RCP: 1-ulp reciprocal (inputs/outputs flushed), used only to RANK faces; the value
 // that is kept, t1, always comes from the IEEE division.
 __device__ __forceinline__ float rcp_approx(float x) {
+#ifdef RFB_EMU
+    return rfb_emu_rcp_approx(x);
+#else
     float r;
     // volatile: keeps the MUFU unconditional so the ranking loop stays branch-free
     asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 
 // Same plane test without the division: returns num and dp.

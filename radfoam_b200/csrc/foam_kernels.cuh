@@ -531,7 +531,11 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     static_assert(HALF_ROW <= 32, "row too wide for one warp pass");
     static_assert((SLOTS & (SLOTS - 1)) == 0, "SLOTS must be a power of two");
 
+#ifdef RFB_EMU
+    float *smem = rfb_emu_dynamic_smem();
+#else
     extern __shared__ __align__(16) float smem[];
+#endif
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARP_FLOATS = (32 * GR + SLOTS * GR + SLOTS + 3) & ~3; // keeps every warp's rows 16-byte aligned
     float *stage = smem + warp * WARP_FLOATS;                          // [32][GR]

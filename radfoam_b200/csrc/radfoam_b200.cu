@@ -15,6 +15,15 @@
 
 #include "foam_kernels.cuh"
 
+// Kernel launch.  In the product this is the <<< >>> launch; the CPU kernel-logic emulator under tests/emu
+// (test infrastructure, never loaded by the product) defines RFB_LAUNCH itself before this file is compiled.
+#ifndef RFB_LAUNCH
+#define RFB_UNPAREN(...) __VA_ARGS__
+#define RFB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (RFB_UNPAREN kernel)<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -159,13 +168,13 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     if (n) {
         int grid = grid_for((uint64_t)n * 32, 256);
         if (p->attr_dtype == RFB_FLOAT16)
-            build_cells_kernel<__half><<<grid, 256, 0, stream>>>(
-                points, reinterpret_cast<const __half *>(attrs), n, A, SR,
-                reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+            RFB_LAUNCH((build_cells_kernel<__half>), grid, 256, 0, stream, points,
+                       reinterpret_cast<const __half *>(attrs), n, A, SR,
+                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
         else
-            build_cells_kernel<float><<<grid, 256, 0, stream>>>(
-                points, reinterpret_cast<const float *>(attrs), n, A, SR,
-                reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+            RFB_LAUNCH((build_cells_kernel<float>), grid, 256, 0, stream, points,
+                       reinterpret_cast<const float *>(attrs), n, A, SR,
+                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
         RFB_LAUNCHED();
     }
     if (need_faces) {
@@ -173,14 +182,14 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
         RFB_CUDA(p->faces.ensure(slots * sizeof(uint2)));
         RFB_CUDA(p->nbr.ensure(slots * sizeof(uint32_t)));
         if (n && caller_diff) {
-            build_faces_from_diff_kernel<<<grid_for((uint64_t)n * 16, 256), 256, 0, stream>>>(
-                reinterpret_cast<const uint2 *>(caller_diff), n, adj, off,
-                reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
+            RFB_LAUNCH((build_faces_from_diff_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream,
+                       reinterpret_cast<const uint2 *>(caller_diff), n, adj, off,
+                       reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
             RFB_LAUNCHED();
         } else if (n) {
-            build_faces_kernel<<<grid_for((uint64_t)n * 16, 256), 256, 0, stream>>>(
-                points, n, adj, off, reinterpret_cast<uint2 *>(p->faces.ptr),
-                reinterpret_cast<uint32_t *>(p->nbr.ptr));
+            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream, points, n, adj,
+                       off, reinterpret_cast<uint2 *>(p->faces.ptr),
+                       reinterpret_cast<uint32_t *>(p->nbr.ptr));
             RFB_LAUNCHED();
         }
     }
@@ -218,10 +227,10 @@ template <typename Faces>
 int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t blocks,
                    cudaStream_t stream) {
     switch (deg) {
-    case 0: forward_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
-    case 1: forward_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
-    case 2: forward_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
-    default: forward_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa); break;
+    case 0: RFB_LAUNCH((forward_kernel<0, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
+    case 1: RFB_LAUNCH((forward_kernel<1, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
+    case 2: RFB_LAUNCH((forward_kernel<2, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
+    default: RFB_LAUNCH((forward_kernel<3, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
     }
     RFB_LAUNCHED();
     return 0;
@@ -231,10 +240,10 @@ template <typename Faces>
 int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape,
                           uint32_t blocks, cudaStream_t stream) {
     switch (deg) {
-    case 0: forward_record_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
-    case 1: forward_record_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
-    case 2: forward_record_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
-    default: forward_record_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(fp, fa, tape); break;
+    case 0: RFB_LAUNCH((forward_record_kernel<0, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
+    case 1: RFB_LAUNCH((forward_record_kernel<1, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
+    case 2: RFB_LAUNCH((forward_record_kernel<2, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
+    default: RFB_LAUNCH((forward_record_kernel<3, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
     }
     RFB_LAUNCHED();
     return 0;
@@ -279,10 +288,10 @@ template <typename Faces>
 int launch_backward(int deg, const BackwardParams &bp, const Faces &fa, uint32_t blocks,
                     cudaStream_t stream) {
     switch (deg) {
-    case 0: backward_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
-    case 1: backward_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
-    case 2: backward_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
-    default: backward_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    case 0: RFB_LAUNCH((backward_kernel<0, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 1: RFB_LAUNCH((backward_kernel<1, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 2: RFB_LAUNCH((backward_kernel<2, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    default: RFB_LAUNCH((backward_kernel<3, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
     }
     RFB_LAUNCHED();
     return 0;
@@ -303,7 +312,7 @@ int launch_backward_cached_one(const BackwardParams &bp, const Faces &fa, const 
         RFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.fetch_or(bit, std::memory_order_relaxed);
     }
-    kernel<<<blocks, kBlock, smem, stream>>>(bp, fa, tape);
+    RFB_LAUNCH((kernel), blocks, kBlock, smem, stream, bp, fa, tape);
     RFB_LAUNCHED();
     return 0;
 }
@@ -358,10 +367,10 @@ template <typename Faces>
 int launch_benchmark(int deg, const BenchmarkParams &bp, const Faces &fa, uint32_t blocks,
                      cudaStream_t stream) {
     switch (deg) {
-    case 0: benchmark_kernel<0, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
-    case 1: benchmark_kernel<1, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
-    case 2: benchmark_kernel<2, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
-    default: benchmark_kernel<3, Faces><<<blocks, kBlock, 0, stream>>>(bp, fa); break;
+    case 0: RFB_LAUNCH((benchmark_kernel<0, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 1: RFB_LAUNCH((benchmark_kernel<1, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 2: RFB_LAUNCH((benchmark_kernel<2, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    default: RFB_LAUNCH((benchmark_kernel<3, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
     }
     RFB_LAUNCHED();
     return 0;
@@ -468,9 +477,9 @@ int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points, uint32_
         return 0;
     if (!points || !point_adjacency || !point_adjacency_offsets || !adjacent_diff)
         return fail("rfb_prefetch_adjacent_diff: NULL argument");
-    rfb::adjacent_diff_kernel<<<grid_for((uint64_t)num_points * 16, 256), 256, 0, (cudaStream_t)stream>>>(
-        points, num_points, point_adjacency, point_adjacency_offsets,
-        reinterpret_cast<uint2 *>(adjacent_diff));
+    RFB_LAUNCH((rfb::adjacent_diff_kernel), grid_for((uint64_t)num_points * 16, 256), 256, 0,
+               (cudaStream_t)stream, points, num_points, point_adjacency, point_adjacency_offsets,
+               reinterpret_cast<uint2 *>(adjacent_diff));
     RFB_LAUNCHED();
     return 0;
 }
@@ -483,8 +492,8 @@ int rfb_nearest_point(const float *points, uint32_t num_points, const float *que
         return fail("rfb_nearest_point: NULL argument");
     if (num_points == 0)
         return fail("rfb_nearest_point: empty point set");
-    rfb::nearest_point_kernel<<<num_queries, 256, 0, (cudaStream_t)stream>>>(points, num_points, queries,
-                                                                              indices);
+    RFB_LAUNCH((rfb::nearest_point_kernel), num_queries, 256, 0, (cudaStream_t)stream, points, num_points,
+               queries, indices);
     RFB_LAUNCHED();
     return 0;
 }
@@ -527,29 +536,30 @@ int rfb_farthest_neighbor(const float *points, uint32_t num_points, const uint32
             cudaGetLastError();
             return fail("rfb_farthest_neighbor: out of device memory for the point mirror");
         }
-        rfb::pad_points_kernel<<<row_grid, 256, 0, stream>>>(points, num_points, mirror);
+        RFB_LAUNCH((rfb::pad_points_kernel), row_grid, 256, 0, stream, points, num_points, mirror);
         const rfb::PaddedPoints padded{mirror};
         if (variant == 1)
-            rfb::farthest_neighbor_kernel<rfb::PaddedPoints, false><<<lane_grid, 256, 0, stream>>>(
-                padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+            RFB_LAUNCH((rfb::farthest_neighbor_kernel<rfb::PaddedPoints, false>), lane_grid, 256, 0, stream,
+                       padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
         else
-            rfb::farthest_neighbor_rows_kernel<rfb::PaddedPoints, false><<<row_grid, 256, 0, stream>>>(
-                padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+            RFB_LAUNCH((rfb::farthest_neighbor_rows_kernel<rfb::PaddedPoints, false>), row_grid, 256, 0,
+                       stream, padded, point_adjacency, point_adjacency_offsets, num_points, indices,
+                       cell_radius);
         g_launches += 2;
         const cudaError_t launched = cudaGetLastError();
         cudaFreeAsync(mirror, stream); // stream-ordered: after the kernels above, also on the error path
         RFB_CUDA(launched);
     } else if (variant == 0) {
-        rfb::farthest_neighbor_kernel<rfb::PackedPoints, true><<<lane_grid, 256, 0, stream>>>(
-            packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCH((rfb::farthest_neighbor_kernel<rfb::PackedPoints, true>), lane_grid, 256, 0, stream,
+                   packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
         RFB_LAUNCHED();
     } else if (variant == 4) {
-        rfb::farthest_neighbor_rows_kernel<rfb::PackedPoints, false><<<row_grid, 256, 0, stream>>>(
-            packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCH((rfb::farthest_neighbor_rows_kernel<rfb::PackedPoints, false>), row_grid, 256, 0, stream,
+                   packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
         RFB_LAUNCHED();
     } else {
-        rfb::farthest_neighbor_kernel<rfb::PackedPoints, false><<<lane_grid, 256, 0, stream>>>(
-            packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
+        RFB_LAUNCH((rfb::farthest_neighbor_kernel<rfb::PackedPoints, false>), lane_grid, 256, 0, stream,
+                   packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
         RFB_LAUNCHED();
     }
     return 0;
@@ -732,13 +742,13 @@ int rfb_trace_backward_finalize(rfb_pipeline *p, uint32_t num_points, float *poi
     int grid = grid_for((uint64_t)num_points * 32, 256);
     int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
     if (p->attr_dtype == RFB_FLOAT16)
-        finalize_grads_kernel<__half><<<grid, 256, 0, stream>>>(
-            reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
-            reinterpret_cast<__half *>(attribute_grad), scrub);
+        RFB_LAUNCH((finalize_grads_kernel<__half>), grid, 256, 0, stream,
+                   reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
+                   reinterpret_cast<__half *>(attribute_grad), scrub);
     else
-        finalize_grads_kernel<float><<<grid, 256, 0, stream>>>(
-            reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
-            reinterpret_cast<float *>(attribute_grad), scrub);
+        RFB_LAUNCH((finalize_grads_kernel<float>), grid, 256, 0, stream,
+                   reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
+                   reinterpret_cast<float *>(attribute_grad), scrub);
     RFB_LAUNCHED();
     return 0;
 }

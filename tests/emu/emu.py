@@ -1,0 +1,164 @@
+"""Driver of the CPU kernel-logic emulator (tests/emu/cuda_emu.h) -- TEST INFRASTRUCTURE ONLY.
+
+Builds the product's C-ABI translation unit (radfoam_b200/csrc/radfoam_b200.cu with its kernels) for host threads
+into tests/emu/libradfoam_b200_emu.so and calls it through the same ctypes table as the product
+(radfoam_b200/_lib.py: SIGNATURES), with numpy arrays standing in for device memory.  The product never loads this
+library (radfoam_b200/_lib.py only knows libradfoam_b200.so) and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from radfoam_b200 import _lib as product_abi  # the ctypes TABLE only; product_abi.load() is never called here
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libradfoam_b200_emu.so")
+_lib = None
+
+
+def _sources():
+    csrc = os.path.join(ROOT, "radfoam_b200", "csrc")
+    return ([os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", "radfoam_b200.h")]
+            + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_lib.cpp")])
+
+
+def build(force: bool = False) -> str:
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in _sources()):
+        return LIB
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-g0", "-DRFB_EMU", "-ffp-contract=off", "-mfma", "-mf16c",
+                           "-fPIC", "-shared", "-pthread", "-w", f"-I{cuda}/include",
+                           os.path.join(HERE, "emu_lib.cpp"), "-o", LIB])
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(build())
+        for name, (restype, argtypes) in product_abi.SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc:
+        raise RuntimeError(load().rfb_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dtype=None):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class EmuPipeline:
+    """numpy-in / numpy-out calls into the emulated library, argument for argument like radfoam_b200.Pipeline."""
+
+    def __init__(self, sh_degree: int, attr_dtype=np.float32):
+        self.lib = load()
+        self.half = np.dtype(attr_dtype) == np.float16
+        self.dtype = np.float16 if self.half else np.float32
+        self.handle = ctypes.c_void_p()
+        _check(self.lib.rfb_create_pipeline(int(sh_degree), 1 if self.half else 0, ctypes.byref(self.handle)))
+        self.attr_dim = int(self.lib.rfb_attribute_dim(self.handle))
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.rfb_destroy_pipeline(self.handle)
+            self.handle = None
+
+    def _scene(self, points, attributes, adjacency, offsets):
+        return (_c(points, np.float32), _c(attributes, self.dtype), _c(adjacency, np.uint32), _c(offsets, np.uint32))
+
+    @staticmethod
+    def _settings(weight_threshold, max_intersections):
+        return product_abi.TraceSettings(0.001 if weight_threshold is None else weight_threshold,
+                                         1024 if max_intersections is None else max_intersections)
+
+    def trace_forward(self, points, attributes, adjacency, offsets, rays, start, depth_quantiles=None,
+                      weight_threshold=None, max_intersections=None, return_contribution=False, scene_version=0,
+                      record_tape=False):
+        pts, att, adj, off = self._scene(points, attributes, adjacency, offsets)
+        rays_c, start_c, dq = _c(rays, np.float32), _c(start, np.uint32), _c(depth_quantiles, np.float32)
+        batch, n, r = rays_c.shape[:-1], pts.shape[0], rays_c.size // 6
+        q = 0 if dq is None else dq.shape[-1]
+        out = {"rgba": np.empty(batch + (4,), self.dtype), "num_intersections": np.empty(batch + (1,), np.uint32)}
+        if dq is not None:
+            out["depth"] = np.empty(batch + (q,), np.float32)
+            out["depth_indices"] = np.empty(batch + (q,), np.uint32)
+        if return_contribution:
+            out["contribution"] = np.zeros((n, 1), self.dtype)
+        width = rays_c.shape[-2] if rays_c.ndim >= 3 else 0
+        opts = product_abi.LaunchOpts(scene_version, width, product_abi.FLAG_RECORD_TAPE if record_tape else 0)
+        settings = self._settings(weight_threshold, max_intersections)
+        self._keep = [pts, att, adj, off, rays_c, start_c, dq]  # the tape key compares these pointers
+        _check(self.lib.rfb_trace_forward(
+            self.handle, ctypes.byref(settings), n, _p(pts), _p(att), adj.size, _p(adj), _p(off), r, _p(rays_c),
+            _p(start_c), q, _p(dq), _p(out["rgba"]), _p(out.get("depth")), _p(out.get("depth_indices")),
+            _p(out["num_intersections"]), _p(out.get("contribution")), ctypes.byref(opts), None))
+        return out
+
+    def trace_backward(self, points, attributes, adjacency, offsets, rays, start, rgba, grad_rgba,
+                       depth_quantiles=None, depth_indices=None, grad_depth=None, ray_error=None,
+                       weight_threshold=None, max_intersections=None, scene_version=0, use_tape=False,
+                       scrub_nonfinite=False):
+        if use_tape:  # same buffers as the recording forward, as the product's Python layer guarantees
+            pts, att, adj, off, rays_c, start_c, dq = self._keep
+        else:
+            pts, att, adj, off = self._scene(points, attributes, adjacency, offsets)
+            rays_c, start_c, dq = _c(rays, np.float32), _c(start, np.uint32), _c(depth_quantiles, np.float32)
+        n, r = pts.shape[0], rays_c.size // 6
+        q = 0 if dq is None else dq.shape[-1]
+        rgba_c, g_c = _c(rgba, self.dtype), _c(grad_rgba, self.dtype)
+        di, gd, err = _c(depth_indices, np.uint32), _c(grad_depth, np.float32), _c(ray_error, self.dtype)
+        out = {"points_grad": np.empty((n, 3), np.float32), "attr_grad": np.empty((n, self.attr_dim), self.dtype)}
+        if err is not None:
+            out["point_error"] = np.zeros((n, 1), self.dtype)
+        width = rays_c.shape[-2] if rays_c.ndim >= 3 else 0
+        flags = (product_abi.FLAG_USE_TAPE if use_tape else 0) | (product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0)
+        opts = product_abi.LaunchOpts(scene_version, width, flags)
+        settings = self._settings(weight_threshold, max_intersections)
+        ray_grad = np.zeros_like(rays_c)
+        _check(self.lib.rfb_trace_backward(
+            self.handle, ctypes.byref(settings), n, _p(pts), _p(att), adj.size, _p(adj), _p(off), r, _p(rays_c),
+            _p(start_c), q, _p(dq), _p(di), _p(rgba_c), _p(g_c), _p(gd), _p(err), _p(ray_grad),
+            _p(out["points_grad"]), _p(out["attr_grad"]), _p(out.get("point_error")), ctypes.byref(opts), None))
+        return out
+
+    def tape_status(self):
+        cap, used, over = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        _check(self.lib.rfb_tape_status(self.handle, ctypes.byref(cap), ctypes.byref(used), ctypes.byref(over)))
+        return {"capacity_chunks": cap.value, "used_chunks": used.value, "overflowed": bool(over.value)}
+
+
+def prefetch_adjacent_diff(points, adjacency, offsets):
+    pts, adj, off = _c(points, np.float32), _c(adjacency, np.uint32), _c(offsets, np.uint32)
+    out = np.zeros((adj.size, 4), np.float16)
+    _check(load().rfb_prefetch_adjacent_diff(_p(pts), pts.shape[0], adj.size, _p(adj), _p(off), _p(out), None))
+    return out
+
+
+def nearest_point(points, queries):
+    pts, q = _c(points, np.float32), _c(queries, np.float32).reshape(-1, 3)
+    out = np.zeros((q.shape[0],), np.uint32)
+    _check(load().rfb_nearest_point(_p(pts), pts.shape[0], _p(q), q.shape[0], _p(out), None))
+    return out
+
+
+def farthest_neighbor(points, adjacency, offsets):
+    pts, adj, off = _c(points, np.float32), _c(adjacency, np.uint32), _c(offsets, np.uint32)
+    idx, radius = np.zeros((pts.shape[0],), np.uint32), np.zeros((pts.shape[0],), np.float32)
+    _check(load().rfb_farthest_neighbor(_p(pts), pts.shape[0], _p(adj), _p(off), _p(idx), _p(radius), None))
+    return idx, radius

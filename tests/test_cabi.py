@@ -73,6 +73,8 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "radfoam_oracle" not in text and "libradfoam_ref" not in text, f
+                # nor the CPU kernel-logic emulator of tests/emu (the RFB_EMU guards in csrc are compile-time only)
+                assert "libradfoam_b200_emu" not in text and "cuda_emu" not in text, f
 
 
 def test_only_tests_smoke_and_bench_touch_the_oracle():

@@ -1,0 +1,170 @@
+"""Kernel LOGIC on the CPU: the product's CUDA sources compiled for host threads by tests/emu (a small emulation of
+warps, shared memory, atomics and the synchronous part of the runtime API) and compared with the oracle.
+
+What this covers without a GPU: the cell walk with the ranked face scan, the compositing / quantile code, both backward
+kernels' gradient routing (MATCH.ANY groups, shared-memory staging, the warp's row cache, direct reductions), the walk
+tape (record, replay, overflow -> re-walk, pool growth), the scene-mirror cache keys, the re-layout kernels, and the
+small CSR passes.  What it does NOT cover: the compiled SASS (nvcc's contraction, libdevice, MUFU.RCP) -- GPU parity is
+tests/test_gpu_*.py.  The emulated library is test infrastructure; the product never loads it and has no fallback."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+import emu  # noqa: E402
+
+TOL = dict(rtol=1e-5, atol=1e-5)   # floats: the emulation and the oracle share libm, so they agree far inside this
+GRAD_TOL = 2e-5                    # of max|ref|; float scatter-adds in thread order
+
+
+def scene(case):
+    f = case.foam
+    return f.points, f.attributes, f.adjacency, f.offsets
+
+
+def check_forward(got, ref):
+    for k in ("num_intersections", "depth_indices"):
+        if k in got:
+            assert np.array_equal(got[k].reshape(-1), np.asarray(ref[k]).reshape(-1)), k   # integers: bit-exact
+    for k in ("rgba", "depth"):
+        if k in got:
+            np.testing.assert_allclose(got[k].astype(np.float32).reshape(-1),
+                                       np.asarray(ref[k], dtype=np.float32).reshape(-1), **TOL)
+
+
+def check_backward(got, ref):
+    for k in ("points_grad", "attr_grad"):
+        assert common.grad_error(got[k].astype(np.float32), np.asarray(ref[k], dtype=np.float32)) <= GRAD_TOL, k
+
+
+@pytest.fixture(scope="module")
+def small_scene():
+    return common.scene_case(num_points=1500, width=48, height=32, q=2)
+
+
+@pytest.mark.parametrize("sh_degree", [0, 1, 2, 3])
+def test_forward_backward_config1_all_degrees(sh_degree):
+    case = common.config1(sh_degree, 2)
+    pipe = emu.EmuPipeline(sh_degree)
+    fwd = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, return_contribution=True)
+    ref = oracle.trace_forward(*scene(case), case.rays, case.start, case.quantiles, return_contribution=True)
+    check_forward(fwd, ref)
+    np.testing.assert_allclose(fwd["contribution"].reshape(-1), np.asarray(ref["contribution"]).reshape(-1),
+                               rtol=1e-4, atol=1e-4)
+    bwd = pipe.trace_backward(*scene(case), case.rays, case.start, fwd["rgba"], case.grad_rgba, case.quantiles,
+                              fwd["depth_indices"], case.grad_depth)
+    rb = oracle.trace_backward(*scene(case), case.rays, case.start, np.asarray(ref["rgba"]), case.grad_rgba,
+                               case.quantiles, np.asarray(ref["depth_indices"]), case.grad_depth)
+    check_backward(bwd, rb)
+
+
+def test_flat_ray_batch_and_no_quantiles():
+    case = common.config1(3, 0)
+    pipe = emu.EmuPipeline(3)
+    rays, start = case.rays.reshape(-1, 6), case.start.reshape(-1)
+    fwd = pipe.trace_forward(*scene(case), rays, start)
+    ref = oracle.trace_forward(*scene(case), rays, start)
+    check_forward(fwd, ref)
+    tiled = pipe.trace_forward(*scene(case), case.rays, case.start)   # 8x4 warp tiles: same result per ray
+    assert np.array_equal(tiled["rgba"].reshape(-1, 4), fwd["rgba"])
+    assert np.array_equal(tiled["num_intersections"].reshape(-1), fwd["num_intersections"].reshape(-1))
+
+
+@pytest.fixture(scope="module")
+def long_walk_scene():
+    return common.scene_case(num_points=8000, width=32, height=16, q=2)   # walks of up to ~50 cells
+
+
+def test_walk_tape_record_replay_overflow_and_growth(long_walk_scene):
+    """First recording overflows the initial pool (one 32-step chunk per warp): the backward must fall back to
+    re-walking (device-side flag) and give the same gradients; the next recording has a grown pool and is replayed."""
+    case = long_walk_scene
+    pipe = emu.EmuPipeline(3)
+    plain = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
+    ref = oracle.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
+    check_forward(plain, ref)
+    assert int(plain["num_intersections"].max()) > 40          # so one chunk per warp cannot hold the walks
+    rb = oracle.trace_backward(*scene(case), case.rays, case.start, np.asarray(ref["rgba"]), case.grad_rgba,
+                               case.quantiles, np.asarray(ref["depth_indices"]), case.grad_depth)
+    args = (None,) * 6
+    rec = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, scene_version=3, record_tape=True)
+    for k in plain:
+        assert np.array_equal(rec[k], plain[k]), k               # recording changes nothing
+    first = pipe.tape_status()
+    assert first["overflowed"] and first["used_chunks"] > first["capacity_chunks"]
+    bwd = pipe.trace_backward(*args, rec["rgba"], case.grad_rgba, None, rec["depth_indices"], case.grad_depth,
+                              scene_version=3, use_tape=True)
+    check_backward(bwd, rb)                                      # overflowed tape -> the re-walk kernel did the work
+    rec = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, scene_version=3, record_tape=True)
+    second = pipe.tape_status()
+    assert not second["overflowed"] and second["capacity_chunks"] >= first["used_chunks"]
+    assert second["used_chunks"] == first["used_chunks"]
+    replay = pipe.trace_backward(*args, rec["rgba"], case.grad_rgba, None, rec["depth_indices"], case.grad_depth,
+                                 scene_version=3, use_tape=True)
+    check_backward(replay, rb)
+    # a stale tape (other scene version) must not be replayed: still correct through the re-walk path
+    stale = pipe.trace_backward(*scene(case), case.rays, case.start, rec["rgba"], case.grad_rgba, case.quantiles,
+                                rec["depth_indices"], case.grad_depth, scene_version=4, use_tape=False)
+    check_backward(stale, rb)
+
+
+def test_direct_backward_mode_and_point_error(small_scene, monkeypatch):
+    case = small_scene
+    rng = np.random.default_rng(5)
+    ray_error = rng.uniform(0, 1, size=case.rays.shape[:-1] + (1,)).astype(np.float32)
+    ref = oracle.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
+    rb = oracle.trace_backward(*scene(case), case.rays, case.start, np.asarray(ref["rgba"]), case.grad_rgba,
+                               case.quantiles, np.asarray(ref["depth_indices"]), case.grad_depth, ray_error=ray_error)
+    for mode in ("cached", "direct"):
+        monkeypatch.setenv("RFB_BWD_MODE", mode)
+        pipe = emu.EmuPipeline(3)
+        fwd = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
+        bwd = pipe.trace_backward(*scene(case), case.rays, case.start, fwd["rgba"], case.grad_rgba, case.quantiles,
+                                  fwd["depth_indices"], case.grad_depth, ray_error=ray_error)
+        check_backward(bwd, rb)
+        np.testing.assert_allclose(bwd["point_error"].reshape(-1), np.asarray(rb["point_error"]).reshape(-1),
+                                   rtol=1e-4, atol=1e-5)
+
+
+def test_half_precision_attributes():
+    case = common.config1(3, 2)
+    f = case.foam
+    attrs = f.attributes.astype(np.float16)
+    pipe = emu.EmuPipeline(3, np.float16)
+    fwd = pipe.trace_forward(f.points, attrs, f.adjacency, f.offsets, case.rays, case.start, case.quantiles)
+    ref = oracle.trace_forward(f.points, attrs, f.adjacency, f.offsets, case.rays, case.start, case.quantiles)
+    assert fwd["rgba"].dtype == np.float16
+    for k in ("num_intersections", "depth_indices"):
+        assert np.array_equal(fwd[k].reshape(-1), np.asarray(ref[k]).reshape(-1))
+    np.testing.assert_allclose(fwd["rgba"].astype(np.float32).reshape(-1),
+                               np.asarray(ref["rgba"], dtype=np.float32).reshape(-1), rtol=2e-3, atol=1e-3)
+
+
+def test_small_csr_passes_bit_exact(small_scene):
+    f = small_scene.foam
+    assert np.array_equal(emu.prefetch_adjacent_diff(f.points, f.adjacency, f.offsets).view(np.uint16),
+                          oracle.prefetch_adjacent_diff(f.points, f.adjacency, f.offsets).view(np.uint16))
+    for g in (f, common.farthest_edge_case()):
+        idx, radius = emu.farthest_neighbor(g.points, g.adjacency, g.offsets)
+        ref_idx, ref_radius = oracle.farthest_neighbor(g.points, g.adjacency, g.offsets)
+        assert np.array_equal(idx, ref_idx)
+        common.assert_same_floats(radius, ref_radius)
+    rng = np.random.default_rng(1)
+    queries = rng.normal(0, 2, size=(9, 3)).astype(np.float32)
+    d2 = ((f.points[None].astype(np.float64) - queries[:, None].astype(np.float64)) ** 2).sum(-1)
+    assert np.array_equal(emu.nearest_point(f.points, queries), d2.argmin(axis=1).astype(np.uint32))
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2", "4"])
+def test_farthest_neighbor_variants_bit_exact(variant, monkeypatch):
+    monkeypatch.setenv("RFB_FARTHEST_VARIANT", variant)
+    g = common.farthest_edge_case()
+    idx, radius = emu.farthest_neighbor(g.points, g.adjacency, g.offsets)
+    ref_idx, ref_radius = oracle.farthest_neighbor(g.points, g.adjacency, g.offsets)
+    assert np.array_equal(idx, ref_idx)
+    common.assert_same_floats(radius, ref_radius)
