@@ -55,6 +55,15 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 #endif
 }
 
+// 8-byte variant (used by the pooled backward, whose lanes own 6 consecutive floats of a row)
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
+#ifdef RFB_EMU
+    rfb_emu_red_add_v2(addr, a, b);
+#else
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------- SH basis
 // Real SH basis of the (unit) direction; same formulas and evaluation order as
 // sh_coefficients<deg>() (sh_utils.cuh:34-70) so nvcc contracts them alike.

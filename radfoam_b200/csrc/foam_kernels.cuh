@@ -745,6 +745,311 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     }
 }
 
+// ---- backward, pooled rows (EXPERIMENT, not the default: RFB_BWD_VARIANT=4..6; functionally checked on the CPU
+// emulator, tests/test_emu_kernels.py, not yet measured on a B200)
+// tests/tools/tape_stats.py on a scene with the bench's rays/points ratio: 40 % of the composited lane-steps sit in
+// same-cell groups of fewer than 6 lanes, which the kernel above reduces directly and which produce 78 % of its
+// 16-byte reductions; another 15 % are the per-step position-gradient reductions.  A 16-row cache fed by EVERY group
+// would issue 0.29x the reductions (32 rows: 0.22x) -- but only if a group costs far less than one serial warp round.
+// This kernel changes three things:
+//  * a lane's record is compact: (dL/drgb, dL/dsigma | position gradient) = 32 bytes in shared memory, plus the
+//    ray's SH basis (64 bytes, written once).  The row is rank one in (basis x dL/drgb), so it is expanded while it is
+//    summed instead of being staged as 52 floats;
+//  * the record of cell i is completed by the position gradient that the walk hands over one composited cell later
+//    (quirk A.5.1) and only then routed, so position gradients ride in the row (floats 49..51) instead of costing a
+//    reduction of their own; the last cell's record leaves with a zero position gradient, as upstream never flushes it;
+//  * groups are summed by QUARTER warps, four groups per round: lane `sub` of a quarter owns SH coefficients
+//    k = 2 sub, 2 sub + 1 (6 floats), lane 0 also the 4 trailing floats.  Groups of >= 8 (>= 16) lanes are split over
+//    2 (4) quarters by lane range and the partial rows are combined by shuffles.  Every group goes through the
+//    warp's row cache (SLOTS rows, direct-mapped); two groups of one round that hash to the same row are not
+//    scheduled together.
+template <int DEG, typename Faces, int SLOTS, int MIN_BLOCKS, bool REPLAY>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+    backward_pooled_kernel(const BackwardParams p, const Faces fa, const Tape tape) {
+    if (tape.pool != nullptr) {
+        const bool overflowed = tape.ctrl[1] != 0u;
+        if (REPLAY == overflowed)
+            return;
+    }
+    constexpr int GR = grad_row(DEG);
+    constexpr int SR = sh_row(DEG);
+    constexpr int NK = sh_dim(DEG);
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(DEG == 3, "lane ownership (6 floats per lane, 8 lanes) is laid out for 16 SH coefficients");
+    static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS <= 32, "SLOTS: power of two, at most 32");
+
+#ifdef RFB_EMU
+    float *smem = rfb_emu_dynamic_smem();
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, quarter = lane >> 3;
+    constexpr int WARP_FLOATS = 32 * 8 + 32 * 16 + SLOTS * GR + SLOTS;
+    float *rec = smem + warp * WARP_FLOATS;                              // [32][8]  (g0 g1 g2 ds | gx gy gz 0)
+    float *bas = rec + 32 * 8;                                           // [32][16] SH basis of the lane's ray
+    float *cache = bas + 32 * 16;                                        // [SLOTS][GR]
+    uint32_t *tags = reinterpret_cast<uint32_t *>(cache + SLOTS * GR);   // [SLOTS]
+    for (int i = lane; i < SLOTS; i += 32)
+        tags[i] = kNone;
+
+    uint32_t r;
+    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    float sh[NK];
+    BackwardRay st;
+    uint32_t cur = 0;
+    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + warp;
+    uint32_t nrec = 0, last_cell = 0;
+    uint2 rec_a = make_uint2(0u, 0u);
+    if (!done) {
+        backward_ray_setup<DEG>(p, r, ray, sh, st);
+        cur = __ldg(p.start + r);
+        pc = ldg4(p.cells + cur);
+        if (REPLAY) {
+            uint2 pr = tape.per_ray[r];
+            nrec = pr.x;
+            last_cell = pr.y;
+            done = nrec == 0;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NK; ++i)
+            sh[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        bas[lane * 16 + i] = i < NK ? sh[i] : 0.0f;
+    __syncwarp();
+
+    float t0 = 0.0f;
+    uint32_t n = 0;
+    uint32_t chunk_ahead = 0;
+    uint2 rec_b = make_uint2(0u, 0u);
+    auto tape_row = [&](uint32_t chunk_id, uint32_t j) -> uint2 {
+        return j < nrec ? __ldcs(tape.pool + ((uint64_t)chunk_id * kTapeChunk + (j % kTapeChunk)) * 32 + lane)
+                        : make_uint2(last_cell, 0u);
+    };
+    if (REPLAY) {
+        chunk_ahead = tape.table[(uint64_t)gwarp * tape.table_stride];
+        if (!done) {
+            rec_a = tape_row(chunk_ahead, 0);
+            rec_b = tape_row(chunk_ahead, 1);
+        }
+    }
+    uint32_t pend_cell = kNone; // cell of the record waiting in rec[lane] for its position gradient
+    float4 *my_rec = reinterpret_cast<float4 *>(rec + lane * 8);
+    const float4 *rec4 = reinterpret_cast<const float4 *>(rec);
+    const float2 *bas2 = reinterpret_cast<const float2 *>(bas);
+
+    for (uint32_t k = 0;; ++k) {
+        bool c_valid = false;
+        float dL_ds = 0.0f;
+        float dL_drgb[3] = {0.0f, 0.0f, 0.0f};
+        uint32_t new_cell = kNone;
+        bool emit = false;
+        uint32_t emit_cell = kNone;
+
+        bool step = false;
+        float t1 = __int_as_float(0x7f800000);
+        uint32_t nxt = 0;
+        if (REPLAY) {
+            if (((k + 2) % kTapeChunk) == 0)
+                chunk_ahead = tape.table[(uint64_t)gwarp * tape.table_stride + (k + 2) / kTapeChunk];
+            if (!done) {
+                uint2 rec_c = tape_row(chunk_ahead, k + 2);
+                t1 = __uint_as_float(rec_a.y);
+                nxt = rec_b.x;
+                rec_a = rec_b;
+                rec_b = rec_c;
+                step = true;
+            }
+        } else if (!done) {
+            n++;
+            if (n > p.max_steps) {
+                done = true;
+            } else {
+                uint32_t begin, nf;
+                fa.row(cur, begin, nf);
+                uint32_t face = kNone;
+                fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                if (face == kNone) {
+                    done = true;
+                } else {
+                    nxt = fa.neighbour(begin, face);
+                    step = true;
+                }
+            }
+        }
+        if (step) {
+            float4 pn = ldg4(p.cells + nxt);
+            if (t1 > t0) {
+                float rgb[3] = {0.0f, 0.0f, 0.0f};
+                if (pc.w > 1e-6f)
+                    sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * SR, sh, rgb[0], rgb[1], rgb[2]);
+                float w, fx, fy, fz;
+                bool flush;
+                uint32_t flush_idx;
+                bool go = st.cell(cur, pc, pn, t0, t1, rgb, ray, p.weight_threshold, dL_drgb, dL_ds, w, flush,
+                                  flush_idx, fx, fy, fz);
+                if (p.point_error)
+                    add_point_error(p, cur, __fmul_rn(w, st.err));
+                if (flush) { // flush_idx == pend_cell: the waiting record is complete now
+                    my_rec[1] = make_float4(fx, fy, fz, 0.0f);
+                    emit = true;
+                    emit_cell = pend_cell;
+                }
+                c_valid = true;
+                new_cell = cur;
+                done = !go;
+            }
+            t0 = fmaxf(t0, t1);
+            cur = nxt;
+            pc = pn;
+            if (REPLAY && k + 1 >= nrec)
+                done = true;
+        } else if (pend_cell != kNone) {
+            // the ray has ended: its last record leaves without a position gradient (never flushed upstream)
+            my_rec[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            emit = true;
+            emit_cell = pend_cell;
+            pend_cell = kNone;
+        }
+        __syncwarp();
+
+        // ---- warp-collective phase: sum the complete records by cell, four groups per round
+        const unsigned grp = __match_any_sync(FULL, emit ? emit_cell : (0x80000000u | lane));
+        unsigned todo = __ballot_sync(FULL, emit && (uint32_t)(__ffs(grp) - 1) == lane);
+        while (todo) {
+            unsigned my_members = 0, used = 0;
+            uint32_t my_cell = kNone, my_slot = 0;
+            int my_need = 1;
+            bool my_owner = false, any2 = false, any4 = false;
+            int q_next = 0;
+            unsigned pending = todo;
+            while (pending && q_next < 4) {
+                const int leader = __ffs(pending) - 1;
+                const unsigned gmask = __shfl_sync(FULL, grp, leader);
+                const uint32_t cell = __shfl_sync(FULL, emit_cell, leader);
+                const int size = __popc(gmask);
+                const int need = size >= 16 ? 4 : (size >= 8 ? 2 : 1);
+                const int q0 = (q_next + need - 1) & ~(need - 1);
+                const uint32_t slot = (cell * 2654435761u) >> (32 - __builtin_ctz(SLOTS));
+                if (q0 + need > 4 || ((used >> slot) & 1u))
+                    break; // next round (the first candidate of a round always fits)
+                used |= 1u << slot;
+                if ((int)quarter >= q0 && (int)quarter < q0 + need) {
+                    const int j = (int)quarter - q0;
+                    my_members = need == 1 ? gmask : (need == 2 ? gmask & (0xFFFFu << (16 * j)) : gmask & (0xFFu << (8 * j)));
+                    my_cell = cell;
+                    my_slot = slot;
+                    my_need = need;
+                    my_owner = j == 0;
+                }
+                any2 |= need == 2;
+                any4 |= need == 4;
+                q_next = q0 + need;
+                todo &= ~(1u << leader);
+                pending &= ~(1u << leader);
+            }
+            float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
+            for (unsigned mm = my_members; mm; mm &= mm - 1) {
+                const int m = __ffs(mm) - 1;
+                const float4 lo = rec4[2 * m], hi = rec4[2 * m + 1];
+                const float2 b = bas2[m * 8 + sub];
+                a[0] = __fmaf_rn(b.x, lo.x, a[0]);
+                a[1] = __fmaf_rn(b.x, lo.y, a[1]);
+                a[2] = __fmaf_rn(b.x, lo.z, a[2]);
+                a[3] = __fmaf_rn(b.y, lo.x, a[3]);
+                a[4] = __fmaf_rn(b.y, lo.y, a[4]);
+                a[5] = __fmaf_rn(b.y, lo.z, a[5]);
+                x[0] += lo.w;
+                x[1] += hi.x;
+                x[2] += hi.y;
+                x[3] += hi.z;
+            }
+            if (any2 || any4) { // partial rows of a group split over quarters
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float o = __shfl_xor_sync(FULL, a[i], 8);
+                    if (my_need >= 2)
+                        a[i] += o;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float o = __shfl_xor_sync(FULL, x[i], 8);
+                    if (my_need >= 2)
+                        x[i] += o;
+                }
+            }
+            if (any4) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float o = __shfl_xor_sync(FULL, a[i], 16);
+                    if (my_need == 4)
+                        a[i] += o;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float o = __shfl_xor_sync(FULL, x[i], 16);
+                    if (my_need == 4)
+                        x[i] += o;
+                }
+            }
+            // cache update by the owning quarter; lane `sub` holds floats [6 sub, 6 sub + 6), lane 0 also [SR, SR + 4).
+            // A row that has to make room leaves as 13 x 16-byte reductions (the quarter's lanes take float4 i and
+            // i + 8): same sectors per row as the kernel above, not 3 x 8 bytes per lane.
+            const bool update = my_owner && my_cell != kNone;
+            uint32_t tag = kNone;
+            float *crow = cache + my_slot * GR;
+            if (update)
+                tag = tags[my_slot];
+            const bool hit = tag == my_cell;
+            if (update && !hit && tag != kNone) {
+                float *grow = p.acc + (uint64_t)tag * GR;
+                for (int i = (int)sub; i < GR / 4; i += 8) {
+                    const float4 v = *reinterpret_cast<const float4 *>(crow + 4 * i);
+                    red_add_v4(grow + 4 * i, v.x, v.y, v.z, v.w);
+                }
+            }
+            __syncwarp(); // the old row and its tag have been read
+            if (update) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                    crow[6 * sub + i] = hit ? crow[6 * sub + i] + a[i] : a[i];
+                if (sub == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        crow[SR + i] = hit ? crow[SR + i] + x[i] : x[i];
+                    tags[my_slot] = my_cell;
+                }
+            }
+            __syncwarp();
+        }
+        // the step's own record starts waiting (after the phase above has read the slot)
+        if (c_valid) {
+            my_rec[0] = make_float4(dL_drgb[0], dL_drgb[1], dL_drgb[2], dL_ds);
+            pend_cell = new_cell;
+        }
+        if (!__any_sync(FULL, !done || pend_cell != kNone))
+            break;
+    }
+
+    // drain the cache: quarter q writes rows q, q + 4, ...
+    __syncwarp();
+    for (int slot = (int)quarter; slot < SLOTS; slot += 4) {
+        const uint32_t tag = tags[slot];
+        if (tag == kNone)
+            continue;
+        const float *crow = cache + slot * GR;
+        float *grow = p.acc + (uint64_t)tag * GR;
+        for (int i = (int)sub; i < GR / 4; i += 8) {
+            const float4 v = *reinterpret_cast<const float4 *>(crow + 4 * i);
+            red_add_v4(grow + 4 * i, v.x, v.y, v.z, v.w);
+        }
+    }
+}
+
 // accumulator -> reference-layout gradient outputs (+ optional finite scrub)
 template <typename AttrT>
 __global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t num_points,

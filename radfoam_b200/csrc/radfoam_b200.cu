@@ -330,6 +330,26 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const 
                                                                                      stream);
 }
 
+template <typename Faces, int SLOTS, bool REPLAY>
+int launch_backward_pooled_one(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
+                               cudaStream_t stream) {
+    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * 8 + 32 * 16 + SLOTS * grad_row(3) + SLOTS) * sizeof(float);
+    static_assert(smem <= 48 * 1024, "needs the dynamic shared-memory opt-in");
+    RFB_LAUNCH((backward_pooled_kernel<3, Faces, SLOTS, 5, REPLAY>), blocks, kBlock, smem, stream, bp, fa, tape);
+    RFB_LAUNCHED();
+    return 0;
+}
+
+// EXPERIMENT (RFB_BWD_VARIANT=4/5/6): pooled-row backward, see foam_kernels.cuh.  Same tape protocol as above.
+template <typename Faces, int SLOTS>
+int launch_backward_pooled(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
+                           cudaStream_t stream) {
+    if (tape.pool)
+        if (int rc = launch_backward_pooled_one<Faces, SLOTS, true>(bp, fa, tape, blocks, stream))
+            return rc;
+    return launch_backward_pooled_one<Faces, SLOTS, false>(bp, fa, tape, blocks, stream);
+}
+
 template <int DEG, typename Faces>
 int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, const Tape &tape,
                                uint32_t blocks, cudaStream_t stream) {
@@ -359,7 +379,14 @@ int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, c
     case 0: return launch_backward_cached_deg<0>(0, bp, fa, tape, blocks, stream);
     case 1: return launch_backward_cached_deg<1>(0, bp, fa, tape, blocks, stream);
     case 2: return launch_backward_cached_deg<2>(0, bp, fa, tape, blocks, stream);
-    default: return launch_backward_cached_deg<3>(variant, bp, fa, tape, blocks, stream);
+    default:
+        if (variant == 4)
+            return launch_backward_pooled<Faces, 16>(bp, fa, tape, blocks, stream);
+        if (variant == 5)
+            return launch_backward_pooled<Faces, 32>(bp, fa, tape, blocks, stream);
+        if (variant == 6)
+            return launch_backward_pooled<Faces, 8>(bp, fa, tape, blocks, stream);
+        return launch_backward_cached_deg<3>(variant, bp, fa, tape, blocks, stream);
     }
 }
 

@@ -76,6 +76,11 @@ struct CtaRun {
     float *smem_base = nullptr;
 };
 
+struct Counters { // what the kernels would send to L2 / how many warp collectives they ran, since the last reset
+    std::atomic<uint64_t> red_v4{0}, red_v2{0}, collectives{0};
+};
+extern Counters counters;
+
 extern thread_local CtaRun *run; // the CTA this OS thread is executing
 extern thread_local Fiber *cur;  // the fiber (CUDA thread) that is running
 
@@ -97,6 +102,7 @@ inline std::array<uint64_t, 32> gather(unsigned mask, uint64_t v) {
     r.arrived |= 1u << lane;
     run->progress++;
     if (((r.arrived | w.exited) & mask) == mask) {
+        counters.collectives.fetch_add(1, std::memory_order_relaxed);
         r.ready = true;
         r.readers = popc(r.arrived);
     } else {
@@ -325,10 +331,17 @@ inline __half atomicAdd(__half *p, __half v) {
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline void rfb_emu_red_add_v4(float *p, float a, float b, float c, float d) {
+    emu::counters.red_v4.fetch_add(1, std::memory_order_relaxed);
     atomicAdd(p, a);
     atomicAdd(p + 1, b);
     atomicAdd(p + 2, c);
     atomicAdd(p + 3, d);
+}
+
+inline void rfb_emu_red_add_v2(float *p, float a, float b) {
+    emu::counters.red_v2.fetch_add(1, std::memory_order_relaxed);
+    atomicAdd(p, a);
+    atomicAdd(p + 1, b);
 }
 
 // ---- warp collectives
@@ -356,6 +369,13 @@ inline T __shfl_sync(unsigned mask, T value, int src, int width = 32) {
     auto v = emu::gather(mask, emu::to_bits(value));
     const unsigned lane = emu::cur->t.lane;
     const unsigned from = (lane & ~(unsigned)(width - 1)) | ((unsigned)src & (unsigned)(width - 1));
+    return (mask >> from & 1u) ? emu::from_bits<T>(v[from]) : value;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T value, int lane_mask, int width = 32) {
+    auto v = emu::gather(mask, emu::to_bits(value));
+    const unsigned from = emu::cur->t.lane ^ (unsigned)lane_mask;
+    (void)width;
     return (mask >> from & 1u) ? emu::from_bits<T>(v[from]) : value;
 }
 template <typename T>

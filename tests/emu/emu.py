@@ -162,3 +162,51 @@ def farthest_neighbor(points, adjacency, offsets):
     idx, radius = np.zeros((pts.shape[0],), np.uint32), np.zeros((pts.shape[0],), np.float32)
     _check(load().rfb_farthest_neighbor(_p(pts), pts.shape[0], _p(adj), _p(off), _p(idx), _p(radius), None))
     return idx, radius
+
+
+def tape_records(pipe: EmuPipeline, height: int, width: int):
+    """Decode the walk tape of the last recording forward of an image-shaped batch (debug / analysis only).
+    Returns (cells[W][S][32] uint32, t1[W][S][32] float32, count[W][32] int) in the backward's own layout:
+    W warps (8x4-pixel tiles, 4 per 16x8 CTA), S = longest walk, lane-major; cells == 0xFFFFFFFF past a lane's end."""
+    lib = load()
+    lib.rfe_tape_buffers.restype = ctypes.c_int
+    pool, table, per_ray = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    stride, cap = ctypes.c_uint32(), ctypes.c_uint32()
+    if lib.rfe_tape_buffers(pipe.handle, ctypes.byref(pool), ctypes.byref(table), ctypes.byref(per_ray),
+                            ctypes.byref(stride), ctypes.byref(cap)):
+        raise RuntimeError("no recorded tape")
+    blocks_x, blocks_y = (width + 15) // 16, (height + 7) // 8
+    nwarps = blocks_x * blocks_y * 4
+    pool_a = np.ctypeslib.as_array(ctypes.cast(pool, ctypes.POINTER(ctypes.c_uint32)), (cap.value, 32, 32, 2))
+    table_a = np.ctypeslib.as_array(ctypes.cast(table, ctypes.POINTER(ctypes.c_uint32)), (nwarps, stride.value))
+    per_ray_a = np.ctypeslib.as_array(ctypes.cast(per_ray, ctypes.POINTER(ctypes.c_uint32)), (height * width, 2))
+    count = np.zeros((nwarps, 32), dtype=np.int64)
+    for w in range(nwarps):
+        block, warp = divmod(w, 4)
+        bx, by = block % blocks_x, block // blocks_x
+        for lane in range(32):
+            x, y = bx * 16 + (warp & 1) * 8 + (lane & 7), by * 8 + (warp >> 1) * 4 + (lane >> 3)
+            if x < width and y < height:
+                count[w, lane] = per_ray_a[y * width + x, 0]
+    steps = int(count.max())
+    cells = np.full((nwarps, steps, 32), 0xFFFFFFFF, dtype=np.uint32)
+    t1 = np.zeros((nwarps, steps, 32), dtype=np.float32)
+    for w in range(nwarps):
+        n = int(count[w].max())
+        for c in range((n + 31) // 32):
+            chunk = pool_a[table_a[w, c]]                      # [32 steps][32 lanes][2]
+            hi = min(32, n - 32 * c)
+            cells[w, 32 * c:32 * c + hi] = chunk[:hi, :, 0]
+            t1[w, 32 * c:32 * c + hi] = chunk[:hi, :, 1].view(np.float32)
+        valid = np.arange(steps)[:, None] < count[w][None, :]
+        cells[w][~valid] = 0xFFFFFFFF
+    return cells, t1, count
+
+
+def red_counters(reset: bool = True) -> dict:
+    """16-byte / 8-byte global reductions and warp-collective operations (shuffles, votes, matches, syncs) the
+    emulated kernels executed since the last reset."""
+    v4, v2, coll = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    load().rfe_counters(ctypes.byref(v4), ctypes.byref(v2), ctypes.byref(coll), 1 if reset else 0)
+    return {"red_v4": v4.value, "red_v2": v2.value, "bytes": 16 * v4.value + 8 * v2.value,
+            "warp_collectives": coll.value}

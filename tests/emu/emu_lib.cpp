@@ -5,6 +5,7 @@
 namespace emu {
 thread_local CtaRun *run = nullptr;
 thread_local Fiber *cur = nullptr;
+Counters counters;
 
 void fiber_entry() {
     (*run->body)();
@@ -15,3 +16,28 @@ void fiber_entry() {
 } // namespace emu
 
 #include "../../radfoam_b200/csrc/radfoam_b200.cu"
+
+// Debug accessor for analysis scripts (tests/tools/tape_stats.py): the walk tape of the last recording forward.
+extern "C" int rfe_tape_buffers(rfb_pipeline *p, const void **pool, const void **table, const void **per_ray,
+                                uint32_t *table_stride, uint32_t *capacity_chunks) {
+    if (!p || !p->tape_valid)
+        return 1;
+    *pool = p->tape_pool.ptr;
+    *table = p->tape_table.ptr;
+    *per_ray = p->tape_per_ray.ptr;
+    *table_stride = p->tape_table_stride;
+    *capacity_chunks = p->tape_capacity;
+    return 0;
+}
+
+// Counters of the emulated reductions (16-byte, 8-byte) since the last reset.
+extern "C" void rfe_counters(uint64_t *red_v4, uint64_t *red_v2, uint64_t *collectives, int reset) {
+    *red_v4 = emu::counters.red_v4.load();
+    *red_v2 = emu::counters.red_v2.load();
+    *collectives = emu::counters.collectives.load();
+    if (reset) {
+        emu::counters.red_v4 = 0;
+        emu::counters.red_v2 = 0;
+        emu::counters.collectives = 0;
+    }
+}

@@ -554,3 +554,18 @@ def test_pt_checkpoint_benchmark_loop(torch_cuda, tmp_path):
             torch.cuda.synchronize()
             b = ref_out.cpu().numpy().view(np.uint8).reshape(height, width, 4).astype(np.int32)
             assert np.abs(a - b).max() <= 1 and (a != b).any(axis=-1).mean() < 2e-3
+
+
+# ------------------------------------------------------------------ experimental kernels (opt-in)
+@pytest.mark.skipif(not __import__("os").environ.get("RFB_TEST_EXPERIMENTS"),
+                    reason="experimental backward variants: set RFB_TEST_EXPERIMENTS=1 (emulator-checked on the CPU, "
+                           "tests/test_emu_kernels.py; not part of the shipped path)")
+@pytest.mark.parametrize("variant", ["4", "5", "6"])
+def test_experimental_pooled_backward_matches_reference_kernels(torch_cuda, variant, monkeypatch):
+    monkeypatch.setenv("RFB_BWD_VARIANT", variant)
+    for case in (common.config1(3, 2), common.scene_case(num_points=60000, width=320, height=200)):
+        ref = run_ref_gpu(torch_cuda, case)
+        for tape in (False, True):
+            got = run_ours(torch_cuda, case, tape=tape, repeat=2 if tape else 1)
+            for k in ("points_grad", "attr_grad"):
+                assert common.grad_error(got[k], ref[k]) <= GRAD_TOL, (variant, tape, k)
