@@ -759,10 +759,11 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 //    (quirk A.5.1) and only then routed, so position gradients ride in the row (floats 49..51) instead of costing a
 //    reduction of their own; the last cell's record leaves with a zero position gradient, as upstream never flushes it;
 //  * groups are summed by QUARTER warps, four groups per round: lane `sub` of a quarter owns SH coefficients
-//    k = 2 sub, 2 sub + 1 (6 floats), lane 0 also the 4 trailing floats.  Groups of >= 8 (>= 16) lanes are split over
-//    2 (4) quarters by lane range and the partial rows are combined by shuffles.  Every group goes through the
-//    warp's row cache (SLOTS rows, direct-mapped); two groups of one round that hash to the same row are not
-//    scheduled together.
+//    k = 2 sub, 2 sub + 1 (6 floats), lane 0 also the 4 trailing floats.  A group of >= 16 lanes takes a round of its
+//    own: it is split over the four quarters by lane range and the partial rows are combined by shuffles.  Every
+//    group goes through the warp's row cache (SLOTS rows, direct-mapped); two groups of one round that hash to the
+//    same row are not scheduled together.  The round scheduler reads the groups from a list the leaders publish in
+//    shared memory (no shuffles).
 template <int DEG, typename Faces, int SLOTS, int MIN_BLOCKS, bool REPLAY>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     backward_pooled_kernel(const BackwardParams p, const Faces fa, const Tape tape) {
@@ -784,11 +785,12 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     extern __shared__ __align__(16) float smem[];
 #endif
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, quarter = lane >> 3;
-    constexpr int WARP_FLOATS = 32 * 8 + 32 * 16 + SLOTS * GR + SLOTS;
+    constexpr int WARP_FLOATS = 32 * 8 + 32 * 16 + SLOTS * GR + 64 + SLOTS;
     float *rec = smem + warp * WARP_FLOATS;                              // [32][8]  (g0 g1 g2 ds | gx gy gz 0)
     float *bas = rec + 32 * 8;                                           // [32][16] SH basis of the lane's ray
     float *cache = bas + 32 * 16;                                        // [SLOTS][GR]
-    uint32_t *tags = reinterpret_cast<uint32_t *>(cache + SLOTS * GR);   // [SLOTS]
+    uint2 *glist = reinterpret_cast<uint2 *>(cache + SLOTS * GR);        // [32] (lane mask, cell) of this iteration's groups
+    uint32_t *tags = reinterpret_cast<uint32_t *>(glist + 32);           // [SLOTS]
     for (int i = lane; i < SLOTS; i += 32)
         tags[i] = kNone;
 
@@ -919,38 +921,50 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 
         // ---- warp-collective phase: sum the complete records by cell, four groups per round
         const unsigned grp = __match_any_sync(FULL, emit ? emit_cell : (0x80000000u | lane));
-        unsigned todo = __ballot_sync(FULL, emit && (uint32_t)(__ffs(grp) - 1) == lane);
-        while (todo) {
+        const bool is_leader = emit && (uint32_t)(__ffs(grp) - 1) == lane;
+        const unsigned leaders = __ballot_sync(FULL, is_leader);
+        if (leaders == 0u) {
+            // nothing to route in this iteration
+        } else {
+            // the leaders publish (lane mask, cell) in lane order so that the round scheduler reads them from shared
+            // memory instead of shuffling them
+            if (is_leader)
+                glist[__popc(leaders & ((1u << lane) - 1u))] = make_uint2(grp, emit_cell);
+            __syncwarp();
+        }
+        const int num_groups = __popc(leaders);
+        int next_group = 0;
+        while (next_group < num_groups) {
             unsigned my_members = 0, used = 0;
             uint32_t my_cell = kNone, my_slot = 0;
-            int my_need = 1;
-            bool my_owner = false, any2 = false, any4 = false;
+            bool my_owner = false, split = false;
             int q_next = 0;
-            unsigned pending = todo;
-            while (pending && q_next < 4) {
-                const int leader = __ffs(pending) - 1;
-                const unsigned gmask = __shfl_sync(FULL, grp, leader);
-                const uint32_t cell = __shfl_sync(FULL, emit_cell, leader);
-                const int size = __popc(gmask);
-                const int need = size >= 16 ? 4 : (size >= 8 ? 2 : 1);
-                const int q0 = (q_next + need - 1) & ~(need - 1);
+            while (next_group < num_groups && q_next < 4) {
+                const uint2 g = glist[next_group];
+                const unsigned gmask = g.x;
+                const uint32_t cell = g.y;
+                const bool big = __popc(gmask) >= 16; // split over the four quarters by lane range
                 const uint32_t slot = (cell * 2654435761u) >> (32 - __builtin_ctz(SLOTS));
-                if (q0 + need > 4 || ((used >> slot) & 1u))
+                if ((big && q_next != 0) || ((used >> slot) & 1u))
                     break; // next round (the first candidate of a round always fits)
                 used |= 1u << slot;
-                if ((int)quarter >= q0 && (int)quarter < q0 + need) {
-                    const int j = (int)quarter - q0;
-                    my_members = need == 1 ? gmask : (need == 2 ? gmask & (0xFFFFu << (16 * j)) : gmask & (0xFFu << (8 * j)));
+                if (big) {
+                    my_members = gmask & (0xFFu << (8 * quarter));
                     my_cell = cell;
                     my_slot = slot;
-                    my_need = need;
-                    my_owner = j == 0;
+                    my_owner = quarter == 0;
+                    split = true;
+                    q_next = 4;
+                } else {
+                    if ((int)quarter == q_next) {
+                        my_members = gmask;
+                        my_cell = cell;
+                        my_slot = slot;
+                        my_owner = true;
+                    }
+                    q_next++;
                 }
-                any2 |= need == 2;
-                any4 |= need == 4;
-                q_next = q0 + need;
-                todo &= ~(1u << leader);
-                pending &= ~(1u << leader);
+                next_group++;
             }
             float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
             for (unsigned mm = my_members; mm; mm &= mm - 1) {
@@ -968,32 +982,16 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
                 x[2] += hi.y;
                 x[3] += hi.z;
             }
-            if (any2 || any4) { // partial rows of a group split over quarters
+            if (split) { // partial rows of the four quarters
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    float o = __shfl_xor_sync(FULL, a[i], 8);
-                    if (my_need >= 2)
-                        a[i] += o;
+                    a[i] += __shfl_xor_sync(FULL, a[i], 8);
+                    a[i] += __shfl_xor_sync(FULL, a[i], 16);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float o = __shfl_xor_sync(FULL, x[i], 8);
-                    if (my_need >= 2)
-                        x[i] += o;
-                }
-            }
-            if (any4) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    float o = __shfl_xor_sync(FULL, a[i], 16);
-                    if (my_need == 4)
-                        a[i] += o;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float o = __shfl_xor_sync(FULL, x[i], 16);
-                    if (my_need == 4)
-                        x[i] += o;
+                    x[i] += __shfl_xor_sync(FULL, x[i], 8);
+                    x[i] += __shfl_xor_sync(FULL, x[i], 16);
                 }
             }
             // cache update by the owning quarter; lane `sub` holds floats [6 sub, 6 sub + 6), lane 0 also [SR, SR + 4).
