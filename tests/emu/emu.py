@@ -137,6 +137,24 @@ class EmuPipeline:
             _p(out["points_grad"]), _p(out["attr_grad"]), _p(out.get("point_error")), ctypes.byref(opts), None))
         return out
 
+    def trace_benchmark(self, points, attributes, adjacency, offsets, adjacent_diff, camera, start_point,
+                        weight_threshold=None, max_intersections=None, scene_version=0):
+        pts, att, adj, off = self._scene(points, attributes, adjacency, offsets)
+        diff = _c(adjacent_diff, np.float16)
+        cam = product_abi.Camera()
+        for key in ("position", "forward", "right", "up"):
+            getattr(cam, key)[:] = [float(v) for v in np.asarray(camera[key]).reshape(-1)[:3]]
+        cam.fov, cam.width, cam.height = float(camera["fov"]), int(camera["width"]), int(camera["height"])
+        cam.model = 0 if camera["model"] == "pinhole" else 1
+        start = np.array([start_point], dtype=np.uint32)
+        out = np.zeros((cam.height, cam.width), dtype=np.uint32)
+        opts = product_abi.LaunchOpts(scene_version, 0, 0)
+        settings = self._settings(weight_threshold, max_intersections)
+        _check(self.lib.rfb_trace_benchmark(self.handle, ctypes.byref(settings), pts.shape[0], _p(pts), _p(att),
+                                            _p(adj), _p(off), _p(diff), ctypes.byref(cam), _p(start), _p(out),
+                                            ctypes.byref(opts), None))
+        return out
+
     def tape_status(self):
         cap, used, over = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         _check(self.lib.rfb_tape_status(self.handle, ctypes.byref(cap), ctypes.byref(used), ctypes.byref(over)))

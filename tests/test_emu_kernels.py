@@ -214,3 +214,60 @@ def test_pooled_rows_issue_fewer_reductions(long_walk_scene, monkeypatch):
                             fwd["depth_indices"], case.grad_depth)
         counts[variant] = emu.red_counters()["bytes"]
     assert counts["4"] < 0.85 * counts["0"]   # 0.73 on this 512-ray scene; 0.36 at 100k rays (profiles/r01_emulated_reduction_counts.json)
+
+
+@pytest.mark.parametrize("tag", ["f16", "f32"])
+@pytest.mark.parametrize("model", ["pinhole", "fisheye"])
+def test_trace_benchmark_against_reference_kernel_frames(tag, model):
+    """The benchmark kernel (in-kernel ray generation, caller-supplied half4 offsets, RGBA8 packing) emulated on the
+    CPU vs frames the REFERENCE's own kernel rendered on a B200 (tests/golden/benchmark2k.npz): at most one level on a
+    few pixels (expf of libm vs libdevice before a truncating pack)."""
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "benchmark2k.npz")))
+    cam = {k: z[f"cam_{model}_{k}"] for k in ("position", "forward", "right", "up")}
+    cam.update(fov=float(z[f"cam_{model}_fov"]), width=64, height=48, model=model)
+    diff = emu.prefetch_adjacent_diff(z["points"], z["adjacency"], z["offsets"])
+    assert np.array_equal(diff.view(np.uint16), z["adjacent_diff"].view(np.uint16))
+    attrs = z["attributes_" + tag]
+    pipe = emu.EmuPipeline(3, attrs.dtype)
+    img = pipe.trace_benchmark(z["points"], attrs, z["adjacency"], z["offsets"], diff, cam,
+                               int(z[f"start_{model}"][0]), weight_threshold=0.05)
+    a = img.view(np.uint8).reshape(48, 64, 4).astype(np.int32)
+    b = z[f"image_{tag}_{model}"].view(np.uint8).reshape(48, 64, 4).astype(np.int32)
+    assert np.abs(a - b).max() <= 1
+    assert (a != b).any(axis=-1).mean() < 5e-3
+
+
+import glob  # noqa: E402
+
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith(("benchmark", "farthest")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_emulated_kernels_against_reference_kernel_golden_vectors(path):
+    """The product kernels' logic (CPU emulator) against outputs of the REFERENCE's own kernels on a B200
+    (tests/golden/*.npz): traversal integers bit-exact; floats / gradients to the CPU tolerances of the oracle's own
+    golden test (libm vs libdevice conditioning, tests/common.py)."""
+    z = dict(np.load(path))
+    half = z["attributes"].dtype == np.float16
+    q = z.get("quantiles")
+    kw = dict(weight_threshold=float(z["weight_threshold"]), max_intersections=int(z["max_intersections"]))
+    scene_ = (z["points"], z["attributes"], z["adjacency"], z["offsets"])
+    deg = oracle.sh_degree_of(z["attributes"].shape[-1])
+    pipe = emu.EmuPipeline(deg, z["attributes"].dtype)
+    fwd = pipe.trace_forward(*scene_, z["rays"], z["start"], q, **kw)
+    assert np.array_equal(fwd["num_intersections"].reshape(-1), z["out_num_intersections"].reshape(-1))
+    if q is not None:
+        assert np.array_equal(fwd["depth_indices"].reshape(-1), z["out_depth_indices"].reshape(-1))
+    if half:
+        np.testing.assert_allclose(fwd["rgba"].astype(np.float32), z["out_rgba"].astype(np.float32).reshape(fwd["rgba"].shape),
+                                   rtol=2e-3, atol=1e-3)
+        return
+    ref = {k[4:]: v for k, v in z.items() if k.startswith("out_")}
+    got = {k: v.reshape(np.asarray(ref[k]).shape) for k, v in fwd.items() if k in ref}
+    common.assert_forward_close_cpu(got, ref, z["attributes"])
+    bwd = pipe.trace_backward(*scene_, z["rays"], z["start"], z["out_rgba"], z["grad_rgba"], q,
+                              z.get("out_depth_indices"), z.get("grad_depth"), **kw)
+    for k in ("points_grad", "attr_grad"):
+        assert common.nonfinite_mismatch(bwd[k], ref[k]) == 0
+        assert common.grad_error(bwd[k], ref[k]) <= common.CPU_GRAD_TOL, k
