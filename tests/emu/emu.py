@@ -32,9 +32,11 @@ def build(force: bool = False) -> str:
         return LIB
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    tmp = f"{LIB}.{os.getpid()}.tmp"  # atomic replace: concurrent test processes may build at the same time
     subprocess.check_call([cxx, "-std=c++17", "-O1", "-g0", "-DRFB_EMU", "-ffp-contract=off", "-mfma", "-mf16c",
                            "-fPIC", "-shared", "-pthread", "-w", f"-I{cuda}/include",
-                           os.path.join(HERE, "emu_lib.cpp"), "-o", LIB])
+                           os.path.join(HERE, "emu_lib.cpp"), "-o", tmp])
+    os.replace(tmp, LIB)
     return LIB
 
 
