@@ -1012,13 +1012,22 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
             }
             __syncwarp(); // the old row and its tag have been read
             if (update) {
+                float2 *mine = reinterpret_cast<float2 *>(crow + 6 * sub); // 8-byte aligned: rows are 208 bytes
 #pragma unroll
-                for (int i = 0; i < 6; ++i)
-                    crow[6 * sub + i] = hit ? crow[6 * sub + i] + a[i] : a[i];
+                for (int i = 0; i < 3; ++i) {
+                    float2 v = hit ? mine[i] : make_float2(0.0f, 0.0f);
+                    v.x += a[2 * i];
+                    v.y += a[2 * i + 1];
+                    mine[i] = v;
+                }
                 if (sub == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        crow[SR + i] = hit ? crow[SR + i] + x[i] : x[i];
+                    float4 *tail = reinterpret_cast<float4 *>(crow + SR);
+                    float4 v = hit ? *tail : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    v.x += x[0];
+                    v.y += x[1];
+                    v.z += x[2];
+                    v.w += x[3];
+                    *tail = v;
                     tags[my_slot] = my_cell;
                 }
             }
