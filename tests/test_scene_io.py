@@ -78,3 +78,76 @@ def test_benchmark_cameras_follow_benchmark_py():
     assert torch.equal(cam["up"], -c2w[8, :3, 1]) and torch.equal(cam["forward"], c2w[8, :3, 2])
     assert cam["fov"] == pytest.approx(2 * math.atan(48 / 1200.0)) and cam["model"] == "pinhole"
     assert all(v.is_contiguous() for v in (cam["position"], cam["right"], cam["up"], cam["forward"]))
+
+
+def test_benchmark_fps_loop_on_the_cpu_emulator(monkeypatch, tmp_path):
+    """The FPS loop of scene_io.benchmark_fps (benchmark.py:86-139) end to end without a GPU: a scene saved to .pt and
+    reloaded with fp16 attributes, the kernels emulated on the CPU (tests/emu) behind a stand-in pipeline object, CUDA
+    events / synchronize stubbed; frames must equal the oracle's trace_benchmark up to one level on a few pixels."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+    import emu
+    from oracle import oracle
+    from radfoam_b200 import pipeline as product_pipeline
+
+    f = foam.scene_foam(2000, sh_degree=3)
+    path = tmp_path / "model.pt"
+    scene_io.FoamScene.from_foam(f, device="cpu").save_pt(path)
+    scene = scene_io.FoamScene.load_pt(path, sh_degree=3, attr_dtype=torch.float16, device="cpu")
+
+    def as_u32(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).view(torch.uint32)
+
+    class EmulatedPipeline:
+        def __init__(self):
+            self.inner = emu.EmuPipeline(3, np.float16)
+
+        def prefetch_adjacent_diff(self, points, adjacency, offsets):
+            return torch.from_numpy(emu.prefetch_adjacent_diff(points.numpy(), adjacency.view(torch.int32).numpy().view(np.uint32),
+                                                               offsets.view(torch.int32).numpy().view(np.uint32)))
+
+        def trace_benchmark(self, points, attributes, adjacency, offsets, adjacent_diff, camera, start_point, output,
+                            weight_threshold=None):
+            cam = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in camera.items()}
+            img = self.inner.trace_benchmark(points.numpy(), attributes.numpy(), adjacency.view(torch.int32).numpy().view(np.uint32),
+                                             offsets.view(torch.int32).numpy().view(np.uint32), adjacent_diff.numpy(), cam,
+                                             int(start_point.view(torch.int32).item()), weight_threshold=weight_threshold)
+            output.view(torch.int32).copy_(torch.from_numpy(img.view(np.int32)))
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(product_pipeline, "nearest_point",
+                        lambda points, queries: as_u32(emu.nearest_point(points.numpy(), queries.numpy())))
+
+    width, height, fov = 48, 32, 0.9
+    c2w = torch.zeros((9, 4, 4))
+    for i in range(9):
+        cam = foam.camera_dict((3.0 * np.cos(0.5 * i), 3.0 * np.sin(0.5 * i), 1.2), fov=fov, width=width, height=height)
+        c2w[i, :3, 0], c2w[i, :3, 1] = torch.from_numpy(cam["right"]), -torch.from_numpy(cam["up"])
+        c2w[i, :3, 2], c2w[i, :3, 3] = torch.from_numpy(cam["forward"]), torch.from_numpy(cam["position"])
+    cameras, positions = scene_io.benchmark_cameras(c2w, height / (2 * math.tan(fov / 2)), width, height)
+    res = scene_io.benchmark_fps(EmulatedPipeline(), scene, cameras, positions, n_reps=1)
+    assert res["frames"] == 2 and res["output"].shape == (2, height, width) and res["fps"] > 0
+    points, attributes, adjacency, offsets = (t.numpy() if t.dtype != torch.uint32 else t.view(torch.int32).numpy().view(np.uint32)
+                                              for t in scene.get_trace_data())
+    diff = oracle.prefetch_adjacent_diff(points, adjacency, offsets)
+    for k, camera in enumerate(cameras):
+        cam = {key: (v.numpy() if isinstance(v, torch.Tensor) else v) for key, v in camera.items()}
+        start = foam.nearest_point(points, cam["position"])
+        want = oracle.trace_benchmark(points, attributes, adjacency, offsets, diff, cam, start, weight_threshold=0.05)
+        a = res["output"][k].view(torch.int32).numpy().view(np.uint8).reshape(height, width, 4).astype(np.int32)
+        b = want.view(np.uint8).reshape(height, width, 4).astype(np.int32)
+        assert (b[..., :3].sum(axis=-1) > 0).mean() > 0.05
+        assert np.abs(a - b).max() <= 1 and (a != b).any(axis=-1).mean() < 1e-2
