@@ -45,10 +45,12 @@ fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq
 res["fwd_record_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res["tape"] = pipe.tape_status()
-for v in range(4):
+# 0 shipped; 1-3 neighbouring cache configurations; 4/5/6 the experimental pooled-row kernel (16/32/8 rows)
+for v in (int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5,6").split(",")):
     os.environ["RFB_BWD_VARIANT"] = str(v)
     out = bwd()
     res[f"replay_v{v}_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
+    res[f"replay_v{v}_points_err_vs_direct"] = float((out["points_grad"] - base["points_grad"]).abs().max() / base["points_grad"].abs().max())
     res[f"replay_v{v}_ms"] = timeit(bwd)
     print(v, res[f"replay_v{v}_ms"], flush=True)
 print(json.dumps(res, indent=1))
