@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import common
-from radfoam_b200 import foam, sharded
+from radfoam_b200 import sharded
 
 
 def test_foam_arrays_follow_the_reference_contract():
