@@ -897,6 +897,10 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
                 if (p.point_error)
                     add_point_error(p, cur, __fmul_rn(w, st.err));
                 if (flush) { // flush_idx == pend_cell: the waiting record is complete now
+#ifdef RFB_EMU
+                    if (flush_idx != pend_cell)
+                        __builtin_trap(); // invariant of the record pipeline, checked on the CPU emulator only
+#endif
                     my_rec[1] = make_float4(fx, fy, fz, 0.0f);
                     emit = true;
                     emit_cell = pend_cell;

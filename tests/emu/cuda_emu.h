@@ -185,10 +185,24 @@ inline void run_cta(dim3 grid, dim3 block, uint3 bid, size_t smem_bytes, const s
         f.ctx.uc_link = &c.scheduler;
         makecontext(&f.ctx, fiber_entry, 0);
     }
+    // RFB_EMU_SHUFFLE=<seed>: resume the fibers in a different pseudo-random order on every pass, so that a missing
+    // __syncwarp / __syncthreads between a shared-memory write and another lane's read shows up as a wrong result
+    // (the default lane order 0..31 hides writer-before-reader dependencies)
+    static const char *shuffle_env = std::getenv("RFB_EMU_SHUFFLE");
+    uint64_t rng = shuffle_env ? (uint64_t)std::atoll(shuffle_env) * 0x9E3779B97F4A7C15ull + bid.x + 1 : 0;
+    std::vector<unsigned> order(nthreads);
+    for (unsigned t = 0; t < nthreads; ++t)
+        order[t] = t;
     unsigned remaining = nthreads;
     while (remaining) {
         const uint64_t before = c.progress;
-        for (unsigned t = 0; t < nthreads; ++t) {
+        if (shuffle_env)
+            for (unsigned t = nthreads - 1; t > 0; --t) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[t], order[(rng >> 33) % (t + 1)]);
+            }
+        for (unsigned oi = 0; oi < nthreads; ++oi) {
+            const unsigned t = order[oi];
             Fiber &f = c.fibers[t];
             if (f.done)
                 continue;

@@ -271,3 +271,39 @@ def test_emulated_kernels_against_reference_kernel_golden_vectors(path):
     for k in ("points_grad", "attr_grad"):
         assert common.nonfinite_mismatch(bwd[k], ref[k]) == 0
         assert common.grad_error(bwd[k], ref[k]) <= common.CPU_GRAD_TOL, k
+
+
+@pytest.mark.parametrize("seed", ["1", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "4"])
+def test_backward_under_shuffled_lane_schedules(seed, variant, long_walk_scene, monkeypatch, tmp_path):
+    """A poor man's racecheck for warp-level synchronisation: the emulator resumes the lanes of a CTA in a different
+    pseudo-random order on every scheduling pass (RFB_EMU_SHUFFLE), so a shared-memory read that is not separated from
+    another lane's write by a __syncwarp gives wrong gradients.  Runs in a subprocess: the order is fixed at load."""
+    import subprocess
+    code = f"""
+import os, sys
+sys.path.insert(0, {os.path.dirname(os.path.dirname(__file__))!r}); sys.path.insert(0, {os.path.dirname(__file__)!r})
+sys.path.insert(0, {os.path.join(os.path.dirname(__file__), "emu")!r})
+import numpy as np, common, emu
+from oracle import oracle
+case = common.scene_case(num_points=8000, width=32, height=16, q=2)
+f = case.foam; sc = (f.points, f.attributes, f.adjacency, f.offsets)
+ref = oracle.trace_forward(*sc, case.rays, case.start, case.quantiles)
+rb = oracle.trace_backward(*sc, case.rays, case.start, np.asarray(ref["rgba"]), case.grad_rgba, case.quantiles,
+                           np.asarray(ref["depth_indices"]), case.grad_depth)
+pipe = emu.EmuPipeline(3)
+for _ in range(2):
+    rec = pipe.trace_forward(*sc, case.rays, case.start, case.quantiles, scene_version=5, record_tape=True)
+assert np.array_equal(rec["num_intersections"].reshape(-1), np.asarray(ref["num_intersections"]).reshape(-1))
+for use_tape in (True, False):
+    bwd = pipe.trace_backward(*sc, case.rays, case.start, rec["rgba"], case.grad_rgba, case.quantiles,
+                              rec["depth_indices"], case.grad_depth, scene_version=5) if not use_tape else \
+          pipe.trace_backward(*(None,) * 6, rec["rgba"], case.grad_rgba, None, rec["depth_indices"], case.grad_depth,
+                              scene_version=5, use_tape=True)
+    for k in ("points_grad", "attr_grad"):
+        assert common.grad_error(bwd[k], np.asarray(rb[k])) <= 2e-5, (k, use_tape)
+print("ok")
+"""
+    env = dict(os.environ, RFB_EMU_SHUFFLE=seed, RFB_BWD_VARIANT=variant)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
