@@ -292,6 +292,92 @@ struct PaddedFaces {
             scan_exact(begin, nf, px, py, pz, ray, t1, face);
         }
     }
+    // EXPERIMENT (forward_record_kernel<.., SCAN = 1>, RFB_FWD_VARIANT=1; not the default, not yet measured):
+    // the ranked scan run warp-synchronously -- every lane calls it, `active` false for lanes without a step -- so
+    // that a 4-face chunk in which NO lane has a front face (dp > 0) is skipped after the dp part by a vote.  Such a
+    // chunk only produces q = +inf for every lane, which leaves (best, second, bf) untouched, so the result is the
+    // same.  tests/tools/face_loop_stats.py: 31 % of the warp-level chunk iterations are of that kind.
+    __device__ __forceinline__ void scan_voted(bool active, uint32_t begin, uint32_t nf, float px, float py,
+                                               float pz, const RayGeom &ray, float &t1, uint32_t &face) const {
+        constexpr unsigned FULL = 0xffffffffu;
+        const float kInf = __int_as_float(0x7f800000);
+        const uint32_t my_nf = active ? nf : 0u;
+        const uint32_t max_nf = __reduce_max_sync(FULL, my_nf);
+        const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
+        float best = kInf, second = kInf;
+        uint32_t bf = kNone;
+        for (uint32_t f = 0; f < max_nf; f += 4) {
+            const bool have = f < my_nf;
+            uint2 rec[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+            float dp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            bool front = false;
+            if (have) {
+                uint4 a = ldg4(p + (f >> 1));
+                uint4 b = ldg4(p + (f >> 1) + 1);
+                rec[0] = make_uint2(a.x, a.y);
+                rec[1] = make_uint2(a.z, a.w);
+                rec[2] = make_uint2(b.x, b.y);
+                rec[3] = make_uint2(b.z, b.w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
+                    __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
+                    dp[k] = __fmaf_rn(__low2float(hxy), ray.dx,
+                                      __fmaf_rn(__high2float(hxy), ray.dy, __fmul_rn(__low2float(hzw), ray.dz)));
+                    front |= dp[k] > 0.0f;
+                }
+            }
+            if (!__any_sync(FULL, front))
+                continue; // no lane can leave through any of these four faces
+            if (have) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float num, dpk;
+                    walk_face_parts(rec[k], px, py, pz, ray, num, dpk); // dpk == dp[k] (same expression)
+                    float q = num * rcp_approx(dpk);
+                    q = (dpk > 0.0f) ? q : kInf;
+                    bf = (q < best) ? f + k : bf;
+                    second = fminf(second, fmaxf(best, q));
+                    best = fminf(best, q);
+                }
+            }
+        }
+        if (!active)
+            return;
+        if (best == kInf) { // as in scan(): hull exit, or a front face whose quotient overflowed
+            bool any_front = false;
+            for (uint32_t f = 0; f < nf; f += 4) {
+                uint4 a = ldg4(p + (f >> 1));
+                uint4 b = ldg4(p + (f >> 1) + 1);
+                uint2 rec[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y),
+                                make_uint2(b.z, b.w)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
+                    __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
+                    float dp = __fmaf_rn(__low2float(hxy), ray.dx,
+                                         __fmaf_rn(__high2float(hxy), ray.dy,
+                                                   __fmul_rn(__low2float(hzw), ray.dz)));
+                    any_front |= dp > 0.0f;
+                }
+            }
+            if (!any_front)
+                return;
+            scan_exact(begin, nf, px, py, pz, ray, t1, face);
+            return;
+        }
+        float ab = fabsf(best);
+        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
+        bool clear = (second - best) > margin;
+        if (clear && fabsf(best) < 1e30f) {
+            float t, dp;
+            walk_face(ldg2(faces + begin + bf), px, py, pz, ray, t, dp);
+            t1 = t;
+            face = bf;
+        } else {
+            scan_exact(begin, nf, px, py, pz, ray, t1, face);
+        }
+    }
     __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {
         return __ldg(nbr + begin + face);
     }

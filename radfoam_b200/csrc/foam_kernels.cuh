@@ -368,6 +368,145 @@ __global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardPar
         p.nint[r] = n;
 }
 
+// EXPERIMENT (RFB_FWD_VARIANT=1; not the default, not yet measured on a B200): forward_record_kernel with the face
+// scan run warp-synchronously so that 4-face chunks without a front face for any lane are skipped by a vote
+// (PaddedFaces::scan_voted).  Everything else is a copy of the kernel above; results are identical
+// (tests/test_emu_kernels.py).
+template <int DEG, typename Faces>
+__global__ void __launch_bounds__(kBlock) forward_record_voted_kernel(const ForwardParams p, const Faces fa,
+                                                                const Tape tape) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    uint32_t r;
+    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
+    const bool has_ray = !done;
+
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    float sh[sh_dim(DEG)];
+    uint32_t Q = 0, qi = 0;
+    const float *qv = nullptr;
+    float cq = 0.0f;
+    uint32_t cur = 0;
+    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_ray) {
+        const float *rp = p.rays + 6 * (uint64_t)r;
+        ray.ox = __ldg(rp + 0);
+        ray.oy = __ldg(rp + 1);
+        ray.oz = __ldg(rp + 2);
+        ray.dx = __ldg(rp + 3);
+        ray.dy = __ldg(rp + 4);
+        ray.dz = __ldg(rp + 5);
+        normalize_dir(ray.dx, ray.dy, ray.dz);
+        Q = p.quantiles ? p.num_q : 0u;
+        qv = p.quantiles + (uint64_t)r * p.num_q;
+        cq = Q ? __ldg(qv) : 0.0f;
+        cur = __ldg(p.start + r);
+        pc = ldg4(p.cells + cur);
+    }
+    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
+
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, t0 = 0.0f;
+    uint32_t n = 0, nrec = 0;
+    uint32_t chunk = kTapeNoChunk;
+    for (uint32_t k = 0;; ++k) {
+        if ((k % kTapeChunk) == 0) { // the warp enters a new chunk of steps
+            uint32_t c = kTapeNoChunk;
+            if (lane == 0) {
+                c = atomicAdd(tape.ctrl, 1u);
+                if (c >= tape.capacity || k / kTapeChunk >= tape.table_stride) {
+                    atomicExch(tape.ctrl + 1, 1u);
+                    c = kTapeNoChunk;
+                } else {
+                    tape.table[(uint64_t)gwarp * tape.table_stride + k / kTapeChunk] = c;
+                }
+            }
+            chunk = __shfl_sync(FULL, c, 0);
+        }
+        // the face scan, hoisted out of the divergent region and run by the whole warp
+        bool stepping = !done;
+        uint32_t v_begin = 0, v_nf = 0, v_face = kNone;
+        float v_t1 = __int_as_float(0x7f800000);
+        if (stepping && n + 1 > p.max_steps)
+            stepping = false; // the budget check below ends the ray
+        if (stepping)
+            fa.row(cur, v_begin, v_nf);
+        fa.scan_voted(stepping, v_begin, v_nf, pc.x, pc.y, pc.z, ray, v_t1, v_face);
+        if (!done) {
+            n++;
+            if (n > p.max_steps) {
+                done = true;
+            } else {
+                const uint32_t begin = v_begin, face = v_face;
+                const float t1 = v_t1;
+                if (face == kNone) {
+                    done = true;
+                } else {
+                    if (chunk != kTapeNoChunk) // streaming store: the tape is written once, read once
+                        __stcs(tape.pool + ((uint64_t)chunk * kTapeChunk + (k % kTapeChunk)) * 32 + lane,
+                               make_uint2(cur, __float_as_uint(t1)));
+                    nrec++;
+                    uint32_t nxt = fa.neighbour(begin, face);
+                    float4 pn = ldg4(p.cells + nxt);
+                    if (t1 > t0) {
+                        float s = pc.w;
+                        float r_ = 0.0f, g_ = 0.0f, b_ = 0.0f;
+                        if (s > 1e-6f)
+                            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * sh_row(DEG), sh, r_, g_, b_);
+                        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
+                        float alpha = 1.0f - expf(-s * delta);
+                        float w = __fmul_rn(T, alpha);
+                        if (p.contrib) {
+                            if (p.out_half)
+                                atomicAdd(reinterpret_cast<__half *>(p.contrib) + cur, __float2half_rn(w));
+                            else
+                                atomicAdd(reinterpret_cast<float *>(p.contrib) + cur, w);
+                        }
+                        cr = __fmaf_rn(w, r_, cr);
+                        cg = __fmaf_rn(w, g_, cg);
+                        cb = __fmaf_rn(w, b_, cb);
+                        float Tn = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        while (qi < Q && Tn < cq) {
+                            p.qdepth[(uint64_t)r * Q + qi] = __fadd_rn(t0, __fdiv_rn(logf(__fdiv_rn(T, cq)), s));
+                            p.qidx[(uint64_t)r * Q + qi] = cur;
+                            qi++;
+                            if (qi < Q)
+                                cq = __ldg(qv + qi);
+                        }
+                        T = Tn;
+                        done = !(T > p.weight_threshold);
+                    }
+                    t0 = fmaxf(t0, t1);
+                    cur = nxt;
+                    pc = pn;
+                }
+            }
+        }
+        if (!__any_sync(FULL, !done))
+            break;
+    }
+    if (!has_ray)
+        return;
+    tape.per_ray[r] = make_uint2(nrec, cur);
+    while (qi < Q) {
+        p.qdepth[(uint64_t)r * Q + qi] = -1.0f;
+        p.qidx[(uint64_t)r * Q + qi] = kNone;
+        qi++;
+    }
+    float a = __fsub_rn(1.0f, T);
+    if (p.out_half) {
+        __half2 lo = __floats2half2_rn(cr, cg), hi = __floats2half2_rn(cb, a);
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t *>(&lo);
+        v.y = *reinterpret_cast<uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(p.rgba)[r] = v;
+    } else {
+        reinterpret_cast<float4 *>(p.rgba)[r] = make_float4(cr, cg, cb, a);
+    }
+    if (p.nint)
+        p.nint[r] = n;
+}
+
 // ------------------------------------------------------------------ backward
 struct BackwardParams {
     const float4 *cells;

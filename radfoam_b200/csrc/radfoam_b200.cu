@@ -239,6 +239,12 @@ int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t b
 template <typename Faces>
 int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape,
                           uint32_t blocks, cudaStream_t stream) {
+    const char *variant_env = getenv("RFB_FWD_VARIANT"); // 1: warp-voted face scan (experiment)
+    if (deg == 3 && variant_env && atoi(variant_env) == 1) {
+        RFB_LAUNCH((forward_record_voted_kernel<3, Faces>), blocks, kBlock, 0, stream, fp, fa, tape);
+        RFB_LAUNCHED();
+        return 0;
+    }
     switch (deg) {
     case 0: RFB_LAUNCH((forward_record_kernel<0, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
     case 1: RFB_LAUNCH((forward_record_kernel<1, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;

@@ -370,6 +370,14 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     return out;
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned value) {
+    auto v = emu::gather(mask, value);
+    unsigned out = 0;
+    for (unsigned l = 0; l < 32; ++l)
+        if ((mask & ~emu::cur->t.warp->exited) >> l & 1u)
+            out = std::max(out, (unsigned)v[l]);
+    return out;
+}
 inline unsigned __match_any_sync(unsigned mask, unsigned value) {
     auto v = emu::gather(mask, value);
     unsigned out = 0;

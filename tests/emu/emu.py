@@ -220,6 +220,7 @@ def tape_records(pipe: EmuPipeline, height: int, width: int):
             t1[w, 32 * c:32 * c + hi] = chunk[:hi, :, 1].view(np.float32)
         valid = np.arange(steps)[:, None] < count[w][None, :]
         cells[w][~valid] = 0xFFFFFFFF
+        t1[w][~valid] = 0.0
     return cells, t1, count
 
 

@@ -307,3 +307,35 @@ print("ok")
     env = dict(os.environ, RFB_EMU_SHUFFLE=seed, RFB_BWD_VARIANT=variant)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_voted_face_scan_forward_is_bit_identical(long_walk_scene, small_scene, monkeypatch):
+    """RFB_FWD_VARIANT=1 (experiment): the recording forward with the warp-voted face scan must reproduce the shipped
+    recording forward bit for bit -- outputs and tape -- on image and edge cases (skipped chunks only ever hold q = inf)."""
+    cases = [long_walk_scene, small_scene, common.config1(3, 2)]
+    rays = common.config1(3, 2).rays.copy()
+    rays[0, 0, 3:] = 0.0
+    rays[0, 1, 3:] = [np.nan, 0, 1]
+    weird = common.config1(3, 2)
+    for case in cases:
+        outs = {}
+        for variant in ("0", "1"):
+            monkeypatch.setenv("RFB_FWD_VARIANT", variant)
+            pipe = emu.EmuPipeline(3)
+            for _ in range(2):
+                rec = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, scene_version=4,
+                                         record_tape=True)
+            h, w = case.rays.shape[:2]
+            outs[variant] = (rec, emu.tape_records(pipe, h, w))
+        for k in outs["0"][0]:
+            assert np.array_equal(outs["0"][0][k].view(np.uint32), outs["1"][0][k].view(np.uint32)), k
+        for a, b in zip(outs["0"][1], outs["1"][1]):
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                  b.view(np.uint32) if b.dtype == np.float32 else b)
+    monkeypatch.setenv("RFB_FWD_VARIANT", "1")
+    pipe = emu.EmuPipeline(3)
+    got = pipe.trace_forward(*scene(weird), rays, weird.start, weird.quantiles, scene_version=4, record_tape=True,
+                             max_intersections=7)
+    ref = oracle.trace_forward(*scene(weird), rays, weird.start, weird.quantiles, max_intersections=7)
+    check_forward_nan_aware = np.array_equal(got["num_intersections"].reshape(-1), np.asarray(ref["num_intersections"]).reshape(-1))
+    assert check_forward_nan_aware
