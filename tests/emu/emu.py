@@ -139,6 +139,36 @@ class EmuPipeline:
             _p(out["points_grad"]), _p(out["attr_grad"]), _p(out.get("point_error")), ctypes.byref(opts), None))
         return out
 
+    def trace_backward_accumulate(self, points, attributes, adjacency, offsets, rays, start, rgba, grad_rgba,
+                                  depth_quantiles=None, depth_indices=None, grad_depth=None,
+                                  weight_threshold=None, max_intersections=None):
+        """The first half of the split backward (ray-sharded multi-GPU use): returns a VIEW of the pipeline's fp32
+        accumulator [N, grad_row] that the caller may sum across ranks before trace_backward_finalize."""
+        pts, att, adj, off = self._scene(points, attributes, adjacency, offsets)
+        rays_c, start_c, dq = _c(rays, np.float32), _c(start, np.uint32), _c(depth_quantiles, np.float32)
+        n, r = pts.shape[0], rays_c.size // 6
+        q = 0 if dq is None else dq.shape[-1]
+        rgba_c, g_c = _c(rgba, self.dtype), _c(grad_rgba, self.dtype)
+        di, gd = _c(depth_indices, np.uint32), _c(grad_depth, np.float32)
+        width = rays_c.shape[-2] if rays_c.ndim >= 3 else 0
+        opts = product_abi.LaunchOpts(0, width, 0)
+        settings = self._settings(weight_threshold, max_intersections)
+        _check(self.lib.rfb_trace_backward_accumulate(
+            self.handle, ctypes.byref(settings), n, _p(pts), _p(att), adj.size, _p(adj), _p(off), r, _p(rays_c),
+            _p(start_c), q, _p(dq), _p(di), _p(rgba_c), _p(g_c), _p(gd), None, None, ctypes.byref(opts), None))
+        ptr, count = ctypes.c_void_p(), ctypes.c_uint64()
+        _check(self.lib.rfb_grad_accumulator(self.handle, ctypes.byref(ptr), ctypes.byref(count)))
+        row = int(self.lib.rfb_grad_row_floats(self.handle))
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), (count.value // row, row))
+
+    def trace_backward_finalize(self, num_points, scrub_nonfinite=False):
+        out = {"points_grad": np.empty((num_points, 3), np.float32),
+               "attr_grad": np.empty((num_points, self.attr_dim), self.dtype)}
+        _check(self.lib.rfb_trace_backward_finalize(
+            self.handle, num_points, _p(out["points_grad"]), _p(out["attr_grad"]),
+            product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
+        return out
+
     def trace_benchmark(self, points, attributes, adjacency, offsets, adjacent_diff, camera, start_point,
                         weight_threshold=None, max_intersections=None, scene_version=0):
         pts, att, adj, off = self._scene(points, attributes, adjacency, offsets)

@@ -339,3 +339,42 @@ def test_voted_face_scan_forward_is_bit_identical(long_walk_scene, small_scene, 
     ref = oracle.trace_forward(*scene(weird), rays, weird.start, weird.quantiles, max_intersections=7)
     check_forward_nan_aware = np.array_equal(got["num_intersections"].reshape(-1), np.asarray(ref["num_intersections"]).reshape(-1))
     assert check_forward_nan_aware
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ray_sharded_split_backward_matches_single_rank(world, long_walk_scene):
+    """The multi-GPU data path on the CPU: the frame is dealt to `world` ranks as interleaved 8-row bands
+    (radfoam_b200.sharded), every rank runs forward + rfb_trace_backward_accumulate on its shard, the accumulators are
+    summed (what the one NCCL all-reduce does) and rfb_trace_backward_finalize writes the gradients -- which must equal
+    the single-rank backward (up to float summation order) and the oracle."""
+    import torch
+
+    from radfoam_b200 import sharded
+
+    case = long_walk_scene
+    height = case.rays.shape[0]
+    ref = oracle.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
+    rb = oracle.trace_backward(*scene(case), case.rays, case.start, np.asarray(ref["rgba"]), case.grad_rgba,
+                               case.quantiles, np.asarray(ref["depth_indices"]), case.grad_depth)
+    single = emu.EmuPipeline(3)
+    fwd1 = single.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
+    total = None
+    pipes = []
+    rgba_parts = []
+    for rank in range(world):
+        rows = sharded.band_rows(height, rank, world).numpy()
+        part = lambda a: None if a is None else np.ascontiguousarray(a[rows])  # noqa: E731
+        pipe = emu.EmuPipeline(3)
+        fwd = pipe.trace_forward(*scene(case), part(case.rays), part(case.start), part(case.quantiles))
+        rgba_parts.append(torch.from_numpy(fwd["rgba"]))
+        acc = pipe.trace_backward_accumulate(*scene(case), part(case.rays), part(case.start), fwd["rgba"],
+                                             part(case.grad_rgba), part(case.quantiles), fwd["depth_indices"],
+                                             part(case.grad_depth))
+        total = acc.copy() if total is None else total + acc
+        pipes.append((pipe, acc))
+    # forward needs no collective: the shards reassemble to the single-rank image bit for bit
+    assert np.array_equal(sharded.unshard_image(rgba_parts, height).numpy(), fwd1["rgba"])
+    for pipe, acc in pipes:      # every rank holds the reduced accumulator after the all-reduce
+        acc[...] = total
+        got = pipe.trace_backward_finalize(case.foam.num_points, scrub_nonfinite=True)
+        check_backward(got, rb)
