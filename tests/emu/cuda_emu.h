@@ -74,6 +74,8 @@ struct CtaRun {
     unsigned live = 0, barrier_waiting = 0;
     uint64_t barrier_generation = 0;
     float *smem_base = nullptr;
+    const void *scheduler_stack = nullptr; // for the sanitizer annotations only
+    size_t scheduler_stack_size = 0;
 };
 
 struct Counters { // what the kernels would send to L2 / how many warp collectives they ran, since the last reset
@@ -85,9 +87,24 @@ extern thread_local CtaRun *run; // the CTA this OS thread is executing
 extern thread_local Fiber *cur;  // the fiber (CUDA thread) that is running
 
 inline unsigned popc(unsigned v) { return (unsigned)__builtin_popcount(v); }
+
+// AddressSanitizer has to be told about stack switches
+#if defined(__SANITIZE_ADDRESS__)
+extern "C" void __sanitizer_start_switch_fiber(void **fake_stack_save, const void *bottom, size_t size);
+extern "C" void __sanitizer_finish_switch_fiber(void *fake_stack_save, const void **bottom_old, size_t *size_old);
+#define RFB_EMU_SWITCH_TO(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define RFB_EMU_SWITCHED(save, bottom_old, size_old) __sanitizer_finish_switch_fiber(save, bottom_old, size_old)
+#else
+#define RFB_EMU_SWITCH_TO(save, bottom, size) ((void)0)
+#define RFB_EMU_SWITCHED(save, bottom_old, size_old) ((void)0)
+#endif
+
 inline void yield() {
     Fiber *self = cur;
+    void *fake = nullptr;
+    RFB_EMU_SWITCH_TO(&fake, run->scheduler_stack, run->scheduler_stack_size);
     swapcontext(&self->ctx, &run->scheduler);
+    RFB_EMU_SWITCHED(fake, nullptr, nullptr);
 }
 
 // All lanes named in `mask` (minus those that exited) exchange one 64-bit value each.
@@ -207,7 +224,10 @@ inline void run_cta(dim3 grid, dim3 block, uint3 bid, size_t smem_bytes, const s
             if (f.done)
                 continue;
             cur = &f;
+            void *fake = nullptr;
+            RFB_EMU_SWITCH_TO(&fake, stacks[t], kFiberStack);
             swapcontext(&c.scheduler, &f.ctx);
+            RFB_EMU_SWITCHED(fake, &c.scheduler_stack, &c.scheduler_stack_size);
             if (f.done)
                 remaining--;
         }

@@ -17,7 +17,10 @@ from radfoam_b200 import _lib as product_abi  # the ctypes TABLE only; product_a
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, "libradfoam_b200_emu.so")
+# RFB_EMU_ASAN=1: an AddressSanitizer build (run python under LD_PRELOAD=libasan.so, ASAN_OPTIONS=detect_leaks=0):
+# out-of-bounds accesses of the kernels to "shared" or "global" memory abort with a report
+ASAN = bool(os.environ.get("RFB_EMU_ASAN"))
+LIB = os.path.join(HERE, "libradfoam_b200_emu_asan.so" if ASAN else "libradfoam_b200_emu.so")
 _lib = None
 
 
@@ -33,7 +36,8 @@ def build(force: bool = False) -> str:
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     tmp = f"{LIB}.{os.getpid()}.tmp"  # atomic replace: concurrent test processes may build at the same time
-    subprocess.check_call([cxx, "-std=c++17", "-O1", "-g0", "-DRFB_EMU", "-ffp-contract=off", "-mfma", "-mf16c",
+    extra = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if ASAN else ["-g0"]
+    subprocess.check_call([cxx, "-std=c++17", "-O1", *extra, "-DRFB_EMU", "-ffp-contract=off", "-mfma", "-mf16c",
                            "-fPIC", "-shared", "-pthread", "-w", f"-I{cuda}/include",
                            os.path.join(HERE, "emu_lib.cpp"), "-o", tmp])
     os.replace(tmp, LIB)

@@ -8,10 +8,13 @@ thread_local Fiber *cur = nullptr;
 Counters counters;
 
 void fiber_entry() {
+    RFB_EMU_SWITCHED(nullptr, &run->scheduler_stack, &run->scheduler_stack_size);
     (*run->body)();
     thread_exit();
     cur->done = true;
-    // returning ends the context: uc_link resumes the scheduler
+    // leave for good (a null save slot tells the sanitizer that this stack is finished); returning ends the context
+    // and uc_link resumes the scheduler
+    RFB_EMU_SWITCH_TO(nullptr, run->scheduler_stack, run->scheduler_stack_size);
 }
 } // namespace emu
 
