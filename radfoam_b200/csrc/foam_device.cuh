@@ -378,6 +378,57 @@ struct PaddedFaces {
             scan_exact(begin, nf, px, py, pz, ray, t1, face);
         }
     }
+    // EXPERIMENT (RFB_FWD_VARIANT=2; not the default, not yet measured): two passes per lane.  Pass 1 computes only
+    // dp of every face (6 of the ~25 instructions per face) and collects the front faces (dp > 0, 46 % of all) in a
+    // bit mask; pass 2 ranks just those, in ascending face order so that "first minimum wins" is preserved.  Rows
+    // longer than 64 faces fall back to scan().  Fewer instructions, more (L1-resident) 8-byte loads.
+    __device__ __forceinline__ void scan_two_pass(uint32_t begin, uint32_t nf, float px, float py, float pz,
+                                                  const RayGeom &ray, float &t1, uint32_t &face) const {
+        if (nf > 64u) {
+            scan(begin, nf, px, py, pz, ray, t1, face);
+            return;
+        }
+        const float kInf = __int_as_float(0x7f800000);
+        const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
+        unsigned long long front = 0ull;
+        for (uint32_t f = 0; f < nf; f += 4) {
+            uint4 a = ldg4(p + (f >> 1));
+            uint4 b = ldg4(p + (f >> 1) + 1);
+            uint2 rec[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y), make_uint2(b.z, b.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
+                __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
+                float dp = __fmaf_rn(__low2float(hxy), ray.dx,
+                                     __fmaf_rn(__high2float(hxy), ray.dy, __fmul_rn(__low2float(hzw), ray.dz)));
+                front |= (unsigned long long)(dp > 0.0f) << (f + k);
+            }
+        }
+        if (front == 0ull)
+            return; // no face with dp > 0: the reference finds none either (hull exit)
+        float best = kInf, second = kInf;
+        uint32_t bf = kNone;
+        for (unsigned long long m = front; m; m &= m - 1) {
+            const uint32_t f = (uint32_t)__ffsll((long long)m) - 1u;
+            float num, dp;
+            walk_face_parts(ldg2(faces + begin + f), px, py, pz, ray, num, dp);
+            float q = num * rcp_approx(dp); // dp > 0 here
+            bf = (q < best) ? f : bf;
+            second = fminf(second, fmaxf(best, q));
+            best = fminf(best, q);
+        }
+        float ab = fabsf(best);
+        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
+        bool clear = (second - best) > margin;
+        if (best != kInf && clear && fabsf(best) < 1e30f) {
+            float t, dp;
+            walk_face(ldg2(faces + begin + bf), px, py, pz, ray, t, dp);
+            t1 = t;
+            face = bf;
+        } else {
+            scan_exact(begin, nf, px, py, pz, ray, t1, face); // near-tie, overflow, NaN: literally the reference's loop
+        }
+    }
     __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {
         return __ldg(nbr + begin + face);
     }

@@ -368,11 +368,12 @@ __global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardPar
         p.nint[r] = n;
 }
 
-// EXPERIMENT (RFB_FWD_VARIANT=1; not the default, not yet measured on a B200): forward_record_kernel with the face
-// scan run warp-synchronously so that 4-face chunks without a front face for any lane are skipped by a vote
-// (PaddedFaces::scan_voted).  Everything else is a copy of the kernel above; results are identical
-// (tests/test_emu_kernels.py).
-template <int DEG, typename Faces>
+// EXPERIMENTS (RFB_FWD_VARIANT=1 / 2; not the default, not yet measured on a B200): forward_record_kernel with
+//   SCAN == 1  the face scan run warp-synchronously so that 4-face chunks without a front face for any lane are skipped
+//              by a vote (PaddedFaces::scan_voted);
+//   SCAN == 2  the two-pass scan (PaddedFaces::scan_two_pass): dp of all faces first, ranking of the front faces only.
+// Everything else is a copy of the kernel above; results are identical (tests/test_emu_kernels.py).
+template <int DEG, typename Faces, int SCAN>
 __global__ void __launch_bounds__(kBlock) forward_record_voted_kernel(const ForwardParams p, const Faces fa,
                                                                 const Tape tape) {
     constexpr unsigned FULL = 0xffffffffu;
@@ -431,7 +432,10 @@ __global__ void __launch_bounds__(kBlock) forward_record_voted_kernel(const Forw
             stepping = false; // the budget check below ends the ray
         if (stepping)
             fa.row(cur, v_begin, v_nf);
-        fa.scan_voted(stepping, v_begin, v_nf, pc.x, pc.y, pc.z, ray, v_t1, v_face);
+        if (SCAN == 1)
+            fa.scan_voted(stepping, v_begin, v_nf, pc.x, pc.y, pc.z, ray, v_t1, v_face);
+        else if (stepping)
+            fa.scan_two_pass(v_begin, v_nf, pc.x, pc.y, pc.z, ray, v_t1, v_face);
         if (!done) {
             n++;
             if (n > p.max_steps) {

@@ -239,9 +239,13 @@ int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t b
 template <typename Faces>
 int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape,
                           uint32_t blocks, cudaStream_t stream) {
-    const char *variant_env = getenv("RFB_FWD_VARIANT"); // 1: warp-voted face scan (experiment)
-    if (deg == 3 && variant_env && atoi(variant_env) == 1) {
-        RFB_LAUNCH((forward_record_voted_kernel<3, Faces>), blocks, kBlock, 0, stream, fp, fa, tape);
+    const char *variant_env = getenv("RFB_FWD_VARIANT"); // experiments: 1 warp-voted face scan, 2 two-pass scan
+    const int fwd_variant = variant_env ? atoi(variant_env) : 0;
+    if (deg == 3 && (fwd_variant == 1 || fwd_variant == 2)) {
+        if (fwd_variant == 1)
+            RFB_LAUNCH((forward_record_voted_kernel<3, Faces, 1>), blocks, kBlock, 0, stream, fp, fa, tape);
+        else
+            RFB_LAUNCH((forward_record_voted_kernel<3, Faces, 2>), blocks, kBlock, 0, stream, fp, fa, tape);
         RFB_LAUNCHED();
         return 0;
     }

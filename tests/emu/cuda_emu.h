@@ -321,6 +321,7 @@ inline unsigned __float_as_uint(float a) { return (unsigned)emu::to_bits(a); }
 inline int __float_as_int(float a) { return (int)emu::to_bits(a); }
 inline int __popc(unsigned a) { return __builtin_popcount(a); }
 inline int __ffs(unsigned a) { return __builtin_ffs((int)a); }
+inline int __ffsll(long long a) { return __builtin_ffsll(a); }
 inline float rfb_emu_rcp_approx(float x) { // rcp.approx.ftz: denormal inputs and results flush to zero
     if (std::fabs(x) < 1.17549435e-38f)
         x = std::copysign(0.0f, x);

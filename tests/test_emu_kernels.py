@@ -309,9 +309,10 @@ print("ok")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
 
-def test_voted_face_scan_forward_is_bit_identical(long_walk_scene, small_scene, monkeypatch):
-    """RFB_FWD_VARIANT=1 (experiment): the recording forward with the warp-voted face scan must reproduce the shipped
-    recording forward bit for bit -- outputs and tape -- on image and edge cases (skipped chunks only ever hold q = inf)."""
+@pytest.mark.parametrize("fwd_variant", ["1", "2"])
+def test_experimental_face_scans_are_bit_identical(fwd_variant, long_walk_scene, small_scene, monkeypatch):
+    """RFB_FWD_VARIANT=1 / 2 (experiments): the recording forward with the warp-voted or the two-pass face scan must
+    reproduce the shipped recording forward bit for bit -- outputs and tape -- on image and edge cases."""
     cases = [long_walk_scene, small_scene, common.config1(3, 2)]
     rays = common.config1(3, 2).rays.copy()
     rays[0, 0, 3:] = 0.0
@@ -319,7 +320,7 @@ def test_voted_face_scan_forward_is_bit_identical(long_walk_scene, small_scene, 
     weird = common.config1(3, 2)
     for case in cases:
         outs = {}
-        for variant in ("0", "1"):
+        for variant in ("0", fwd_variant):
             monkeypatch.setenv("RFB_FWD_VARIANT", variant)
             pipe = emu.EmuPipeline(3)
             for _ in range(2):
@@ -328,11 +329,11 @@ def test_voted_face_scan_forward_is_bit_identical(long_walk_scene, small_scene, 
             h, w = case.rays.shape[:2]
             outs[variant] = (rec, emu.tape_records(pipe, h, w))
         for k in outs["0"][0]:
-            assert np.array_equal(outs["0"][0][k].view(np.uint32), outs["1"][0][k].view(np.uint32)), k
-        for a, b in zip(outs["0"][1], outs["1"][1]):
+            assert np.array_equal(outs["0"][0][k].view(np.uint32), outs[fwd_variant][0][k].view(np.uint32)), k
+        for a, b in zip(outs["0"][1], outs[fwd_variant][1]):
             assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
                                   b.view(np.uint32) if b.dtype == np.float32 else b)
-    monkeypatch.setenv("RFB_FWD_VARIANT", "1")
+    monkeypatch.setenv("RFB_FWD_VARIANT", fwd_variant)
     pipe = emu.EmuPipeline(3)
     got = pipe.trace_forward(*scene(weird), rays, weird.start, weird.quantiles, scene_version=4, record_tape=True,
                              max_intersections=7)

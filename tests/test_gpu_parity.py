@@ -573,12 +573,13 @@ def test_experimental_pooled_backward_matches_reference_kernels(torch_cuda, vari
 
 @pytest.mark.skipif(not __import__("os").environ.get("RFB_TEST_EXPERIMENTS"),
                     reason="experimental forward variant: set RFB_TEST_EXPERIMENTS=1")
-def test_experimental_voted_forward_is_bit_identical(torch_cuda, monkeypatch):
+@pytest.mark.parametrize("fwd_variant", ["1", "2"])
+def test_experimental_forward_scans_are_bit_identical(torch_cuda, fwd_variant, monkeypatch):
     for case in (common.config1(3, 2), common.scene_case(num_points=60000, width=320, height=200),
                  common.scene_case(num_points=60000, width=320, height=200, inside=True)):
         monkeypatch.setenv("RFB_FWD_VARIANT", "0")
         base = run_ours(torch_cuda, case, tape=True, repeat=2)
-        monkeypatch.setenv("RFB_FWD_VARIANT", "1")
+        monkeypatch.setenv("RFB_FWD_VARIANT", fwd_variant)
         got = run_ours(torch_cuda, case, tape=True, repeat=2)
         for k in ("rgba", "depth", "depth_indices", "num_intersections"):
             assert np.array_equal(got[k].view(np.uint32), base[k].view(np.uint32)), k

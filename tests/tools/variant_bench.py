@@ -43,15 +43,19 @@ scene[0].requires_grad_(True)
 pipe.record_tape = True
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res["fwd_record_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
-# experimental recording forward with the warp-voted face scan (RFB_FWD_VARIANT=1): time + bit-identity
-os.environ["RFB_FWD_VARIANT"] = "1"
-voted = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
-res["fwd_record_voted_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
+# experimental recording forwards (RFB_FWD_VARIANT=1 warp-voted face scan, 2 two-pass scan): time + bit-identity
 os.environ["RFB_FWD_VARIANT"] = "0"
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
-res["fwd_record_voted_identical"] = bool(all(torch.equal(voted[k].view(torch.int32) if voted[k].dtype != torch.float16 else voted[k],
-                                                         fwd[k].view(torch.int32) if fwd[k].dtype != torch.float16 else fwd[k])
-                                             for k in ("rgba", "depth", "depth_indices", "num_intersections")))
+for fv, name in ((1, "voted"), (2, "two_pass")):
+    os.environ["RFB_FWD_VARIANT"] = str(fv)
+    alt = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
+    res[f"fwd_record_{name}_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
+    res[f"fwd_record_{name}_identical"] = bool(all(
+        torch.equal(alt[k].view(torch.int32) if alt[k].dtype != torch.float16 else alt[k],
+                    fwd[k].view(torch.int32) if fwd[k].dtype != torch.float16 else fwd[k])
+        for k in ("rgba", "depth", "depth_indices", "num_intersections")))
+os.environ["RFB_FWD_VARIANT"] = "0"
+fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res["tape"] = pipe.tape_status()
 # 0 shipped; 1-3 neighbouring cache configurations; 4/5/6 the experimental pooled-row kernel (16/32/8 rows)
 for v in (int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5,6").split(",")):
