@@ -174,8 +174,16 @@ constexpr size_t kFiberStack = 256 * 1024;
 
 inline void run_cta(dim3 grid, dim3 block, uint3 bid, size_t smem_bytes, const std::function<void()> &body) {
     const unsigned nthreads = block.x * block.y * block.z, nwarps = (nthreads + 31) / 32;
-    static thread_local std::vector<char *> stacks;
+    struct StackPool { // freed when the worker thread of a launch ends; the calling thread keeps and reuses its own
+        std::vector<char *> v;
+        ~StackPool() {
+            for (char *p : v)
+                std::free(p);
+        }
+    };
+    static thread_local StackPool pool;
     static thread_local std::vector<float> smem;
+    std::vector<char *> &stacks = pool.v;
     while (stacks.size() < nthreads)
         stacks.push_back(static_cast<char *>(std::aligned_alloc(64, kFiberStack)));
     smem.assign(smem_bytes / sizeof(float) + 8, 0.0f);
