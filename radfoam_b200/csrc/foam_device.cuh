@@ -327,7 +327,11 @@ struct PaddedFaces {
                     front |= dp[k] > 0.0f;
                 }
             }
-            if (!__any_sync(FULL, front))
+            const bool needed = __any_sync(FULL, front);
+#ifdef RFB_EMU
+            rfb_emu_count_vote(needed); // statistics on the CPU emulator only
+#endif
+            if (!needed)
                 continue; // no lane can leave through any of these four faces
             if (have) {
 #pragma unroll
