@@ -928,11 +928,11 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     extern __shared__ __align__(16) float smem[];
 #endif
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, quarter = lane >> 3;
-    constexpr int WARP_FLOATS = 32 * 8 + 32 * 16 + SLOTS * GR + 64 + SLOTS;
+    constexpr int WARP_FLOATS = 32 * 8 + 32 * 16 + SLOTS * GR + 128 + SLOTS;
     float *rec = smem + warp * WARP_FLOATS;                              // [32][8]  (g0 g1 g2 ds | gx gy gz 0)
     float *bas = rec + 32 * 8;                                           // [32][16] SH basis of the lane's ray
     float *cache = bas + 32 * 16;                                        // [SLOTS][GR]
-    uint2 *glist = reinterpret_cast<uint2 *>(cache + SLOTS * GR);        // [32] (lane mask, cell) of this iteration's groups
+    uint4 *glist = reinterpret_cast<uint4 *>(cache + SLOTS * GR);        // [32] this iteration's groups
     uint32_t *tags = reinterpret_cast<uint32_t *>(glist + 32);           // [SLOTS]
     for (int i = lane; i < SLOTS; i += 32)
         tags[i] = kNone;
@@ -1075,8 +1075,10 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
         } else {
             // the leaders publish (lane mask, cell) in lane order so that the round scheduler reads them from shared
             // memory instead of shuffling them
-            if (is_leader)
-                glist[__popc(leaders & ((1u << lane) - 1u))] = make_uint2(grp, emit_cell);
+            if (is_leader) // (lane mask, cell, cache row, lanes): everything the scheduler needs, computed once
+                glist[__popc(leaders & ((1u << lane) - 1u))] =
+                    make_uint4(grp, emit_cell, (emit_cell * 2654435761u) >> (32 - __builtin_ctz(SLOTS)),
+                               (uint32_t)__popc(grp));
             __syncwarp();
         }
         const int num_groups = __popc(leaders);
@@ -1087,11 +1089,10 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
             bool my_owner = false, split = false;
             int q_next = 0;
             while (next_group < num_groups && q_next < 4) {
-                const uint2 g = glist[next_group];
+                const uint4 g = glist[next_group];
                 const unsigned gmask = g.x;
-                const uint32_t cell = g.y;
-                const bool big = __popc(gmask) >= 16; // split over the four quarters by lane range
-                const uint32_t slot = (cell * 2654435761u) >> (32 - __builtin_ctz(SLOTS));
+                const uint32_t cell = g.y, slot = g.z;
+                const bool big = g.w >= 16u; // split over the four quarters by lane range
                 if ((big && q_next != 0) || ((used >> slot) & 1u))
                     break; // next round (the first candidate of a round always fits)
                 used |= 1u << slot;
@@ -1114,20 +1115,31 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
                 next_group++;
             }
             float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
-            for (unsigned mm = my_members; mm; mm &= mm - 1) {
-                const int m = __ffs(mm) - 1;
-                const float4 lo = rec4[2 * m], hi = rec4[2 * m + 1];
-                const float2 b = bas2[m * 8 + sub];
-                a[0] = __fmaf_rn(b.x, lo.x, a[0]);
-                a[1] = __fmaf_rn(b.x, lo.y, a[1]);
-                a[2] = __fmaf_rn(b.x, lo.z, a[2]);
-                a[3] = __fmaf_rn(b.y, lo.x, a[3]);
-                a[4] = __fmaf_rn(b.y, lo.y, a[4]);
-                a[5] = __fmaf_rn(b.y, lo.z, a[5]);
-                x[0] += lo.w;
-                x[1] += hi.x;
-                x[2] += hi.y;
-                x[3] += hi.z;
+            for (unsigned mm = my_members; mm;) { // two members per trip: the shared-memory loads overlap
+                const int m0 = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const bool two = mm != 0u;
+                const int m1 = two ? __ffs(mm) - 1 : m0;
+                mm &= mm - 1;
+                const float4 lo0 = rec4[2 * m0], hi0 = rec4[2 * m0 + 1];
+                const float2 b0 = bas2[m0 * 8 + sub];
+                float4 lo1 = rec4[2 * m1], hi1 = rec4[2 * m1 + 1];
+                float2 b1 = bas2[m1 * 8 + sub];
+                if (!two) { // the second slot repeats the first: contribute zeros
+                    b1 = make_float2(0.0f, 0.0f);
+                    lo1.w = 0.0f;
+                    hi1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                a[0] = __fmaf_rn(b1.x, lo1.x, __fmaf_rn(b0.x, lo0.x, a[0]));
+                a[1] = __fmaf_rn(b1.x, lo1.y, __fmaf_rn(b0.x, lo0.y, a[1]));
+                a[2] = __fmaf_rn(b1.x, lo1.z, __fmaf_rn(b0.x, lo0.z, a[2]));
+                a[3] = __fmaf_rn(b1.y, lo1.x, __fmaf_rn(b0.y, lo0.x, a[3]));
+                a[4] = __fmaf_rn(b1.y, lo1.y, __fmaf_rn(b0.y, lo0.y, a[4]));
+                a[5] = __fmaf_rn(b1.y, lo1.z, __fmaf_rn(b0.y, lo0.z, a[5]));
+                x[0] += lo0.w + lo1.w;
+                x[1] += hi0.x + hi1.x;
+                x[2] += hi0.y + hi1.y;
+                x[3] += hi0.z + hi1.z;
             }
             if (split) { // partial rows of the four quarters
 #pragma unroll

@@ -343,7 +343,7 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const 
 template <typename Faces, int SLOTS, bool REPLAY>
 int launch_backward_pooled_one(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
                                cudaStream_t stream) {
-    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * 8 + 32 * 16 + SLOTS * grad_row(3) + 64 + SLOTS) * sizeof(float);
+    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * 8 + 32 * 16 + SLOTS * grad_row(3) + 128 + SLOTS) * sizeof(float);
     static_assert(smem <= 48 * 1024, "needs the dynamic shared-memory opt-in");
     RFB_LAUNCH((backward_pooled_kernel<3, Faces, SLOTS, 5, REPLAY>), blocks, kBlock, smem, stream, bp, fa, tape);
     RFB_LAUNCHED();
