@@ -1115,31 +1115,21 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
                 next_group++;
             }
             float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
-            for (unsigned mm = my_members; mm;) { // two members per trip: the shared-memory loads overlap
-                const int m0 = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const bool two = mm != 0u;
-                const int m1 = two ? __ffs(mm) - 1 : m0;
-                mm &= mm - 1;
-                const float4 lo0 = rec4[2 * m0], hi0 = rec4[2 * m0 + 1];
-                const float2 b0 = bas2[m0 * 8 + sub];
-                float4 lo1 = rec4[2 * m1], hi1 = rec4[2 * m1 + 1];
-                float2 b1 = bas2[m1 * 8 + sub];
-                if (!two) { // the second slot repeats the first: contribute zeros
-                    b1 = make_float2(0.0f, 0.0f);
-                    lo1.w = 0.0f;
-                    hi1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
-                a[0] = __fmaf_rn(b1.x, lo1.x, __fmaf_rn(b0.x, lo0.x, a[0]));
-                a[1] = __fmaf_rn(b1.x, lo1.y, __fmaf_rn(b0.x, lo0.y, a[1]));
-                a[2] = __fmaf_rn(b1.x, lo1.z, __fmaf_rn(b0.x, lo0.z, a[2]));
-                a[3] = __fmaf_rn(b1.y, lo1.x, __fmaf_rn(b0.y, lo0.x, a[3]));
-                a[4] = __fmaf_rn(b1.y, lo1.y, __fmaf_rn(b0.y, lo0.y, a[4]));
-                a[5] = __fmaf_rn(b1.y, lo1.z, __fmaf_rn(b0.y, lo0.z, a[5]));
-                x[0] += lo0.w + lo1.w;
-                x[1] += hi0.x + hi1.x;
-                x[2] += hi0.y + hi1.y;
-                x[3] += hi0.z + hi1.z;
+            for (unsigned mm = my_members; mm; mm &= mm - 1) {
+                // (two members per trip was tried: +12 live registers -> 48-72 bytes of spill at 5 CTAs/SM)
+                const int m = __ffs(mm) - 1;
+                const float4 lo = rec4[2 * m], hi = rec4[2 * m + 1];
+                const float2 b = bas2[m * 8 + sub];
+                a[0] = __fmaf_rn(b.x, lo.x, a[0]);
+                a[1] = __fmaf_rn(b.x, lo.y, a[1]);
+                a[2] = __fmaf_rn(b.x, lo.z, a[2]);
+                a[3] = __fmaf_rn(b.y, lo.x, a[3]);
+                a[4] = __fmaf_rn(b.y, lo.y, a[4]);
+                a[5] = __fmaf_rn(b.y, lo.z, a[5]);
+                x[0] += lo.w;
+                x[1] += hi.x;
+                x[2] += hi.y;
+                x[3] += hi.z;
             }
             if (split) { // partial rows of the four quarters
 #pragma unroll
