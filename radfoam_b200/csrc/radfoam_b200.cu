@@ -340,24 +340,25 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const 
                                                                                      stream);
 }
 
-template <typename Faces, int SLOTS, bool REPLAY>
+template <typename Faces, int SLOTS, int MIN_GROUP, bool REPLAY>
 int launch_backward_pooled_one(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
                                cudaStream_t stream) {
     constexpr size_t smem = (size_t)(kBlock / 32) * (32 * 8 + 32 * 16 + SLOTS * grad_row(3) + 128 + SLOTS) * sizeof(float);
     static_assert(smem <= 48 * 1024, "needs the dynamic shared-memory opt-in");
-    RFB_LAUNCH((backward_pooled_kernel<3, Faces, SLOTS, 5, REPLAY>), blocks, kBlock, smem, stream, bp, fa, tape);
+    RFB_LAUNCH((backward_pooled_kernel<3, Faces, SLOTS, MIN_GROUP, 5, REPLAY>), blocks, kBlock, smem, stream, bp, fa,
+               tape);
     RFB_LAUNCHED();
     return 0;
 }
 
-// EXPERIMENT (RFB_BWD_VARIANT=4/5/6): pooled-row backward, see foam_kernels.cuh.  Same tape protocol as above.
-template <typename Faces, int SLOTS>
+// EXPERIMENT (RFB_BWD_VARIANT=4..8): pooled-row backward, see foam_kernels.cuh.  Same tape protocol as above.
+template <typename Faces, int SLOTS, int MIN_GROUP>
 int launch_backward_pooled(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
                            cudaStream_t stream) {
     if (tape.pool)
-        if (int rc = launch_backward_pooled_one<Faces, SLOTS, true>(bp, fa, tape, blocks, stream))
+        if (int rc = launch_backward_pooled_one<Faces, SLOTS, MIN_GROUP, true>(bp, fa, tape, blocks, stream))
             return rc;
-    return launch_backward_pooled_one<Faces, SLOTS, false>(bp, fa, tape, blocks, stream);
+    return launch_backward_pooled_one<Faces, SLOTS, MIN_GROUP, false>(bp, fa, tape, blocks, stream);
 }
 
 template <int DEG, typename Faces>
@@ -391,11 +392,15 @@ int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, c
     case 2: return launch_backward_cached_deg<2>(0, bp, fa, tape, blocks, stream);
     default:
         if (variant == 4)
-            return launch_backward_pooled<Faces, 16>(bp, fa, tape, blocks, stream);
+            return launch_backward_pooled<Faces, 16, 1>(bp, fa, tape, blocks, stream);
         if (variant == 5)
-            return launch_backward_pooled<Faces, 32>(bp, fa, tape, blocks, stream);
+            return launch_backward_pooled<Faces, 32, 1>(bp, fa, tape, blocks, stream);
         if (variant == 6)
-            return launch_backward_pooled<Faces, 8>(bp, fa, tape, blocks, stream);
+            return launch_backward_pooled<Faces, 8, 1>(bp, fa, tape, blocks, stream);
+        if (variant == 7) // lone lanes reduce directly
+            return launch_backward_pooled<Faces, 16, 2>(bp, fa, tape, blocks, stream);
+        if (variant == 8)
+            return launch_backward_pooled<Faces, 8, 2>(bp, fa, tape, blocks, stream);
         return launch_backward_cached_deg<3>(variant, bp, fa, tape, blocks, stream);
     }
 }

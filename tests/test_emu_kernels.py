@@ -170,7 +170,7 @@ def test_farthest_neighbor_variants_bit_exact(variant, monkeypatch):
     common.assert_same_floats(radius, ref_radius)
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5", "6"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5", "6", "7", "8"])
 def test_backward_variants_incl_pooled_rows(variant, long_walk_scene, monkeypatch):
     """RFB_BWD_VARIANT: 1-3 neighbouring cache configurations, 4-6 the experimental pooled-row kernel (compact records,
     quarter-warp group sums, position gradients inside the row).  Re-walk and tape replay, image and flat batches."""
@@ -274,7 +274,7 @@ def test_emulated_kernels_against_reference_kernel_golden_vectors(path):
 
 
 @pytest.mark.parametrize("seed", ["1", "2", "3"])
-@pytest.mark.parametrize("variant", ["0", "4"])
+@pytest.mark.parametrize("variant", ["0", "4", "7"])
 def test_backward_under_shuffled_lane_schedules(seed, variant, long_walk_scene, monkeypatch, tmp_path):
     """A poor man's racecheck for warp-level synchronisation: the emulator resumes the lanes of a CTA in a different
     pseudo-random order on every scheduling pass (RFB_EMU_SHUFFLE), so a shared-memory read that is not separated from

@@ -560,7 +560,7 @@ def test_pt_checkpoint_benchmark_loop(torch_cuda, tmp_path):
 @pytest.mark.skipif(not __import__("os").environ.get("RFB_TEST_EXPERIMENTS"),
                     reason="experimental backward variants: set RFB_TEST_EXPERIMENTS=1 (emulator-checked on the CPU, "
                            "tests/test_emu_kernels.py; not part of the shipped path)")
-@pytest.mark.parametrize("variant", ["4", "5", "6"])
+@pytest.mark.parametrize("variant", ["4", "5", "6", "7", "8"])
 def test_experimental_pooled_backward_matches_reference_kernels(torch_cuda, variant, monkeypatch):
     monkeypatch.setenv("RFB_BWD_VARIANT", variant)
     for case in (common.config1(3, 2), common.scene_case(num_points=60000, width=320, height=200)):

@@ -16,7 +16,8 @@ import emu  # noqa: E402
 
 NAMES = {0: "shipped: 4-row cache, groups >= 6 lanes", 1: "8-row cache, groups >= 8", 2: "4 rows, groups >= 5",
          3: "2 rows, groups >= 6", 6: "pooled rows, 8-row cache", 4: "pooled rows, 16-row cache",
-         5: "pooled rows, 32-row cache"}
+         5: "pooled rows, 32-row cache", 7: "pooled rows, 16-row cache, lone lanes direct",
+         8: "pooled rows, 8-row cache, lone lanes direct"}
 
 
 def main():
@@ -28,7 +29,7 @@ def main():
     scene = (f.points, f.attributes, f.adjacency, f.offsets)
     res = {"points": int(f.num_points), "rays": width * height, "variants": {}}
     base = None
-    for variant in (0, 1, 2, 3, 6, 4, 5):
+    for variant in (0, 1, 2, 3, 6, 4, 5, 8, 7):
         os.environ["RFB_BWD_VARIANT"] = str(variant)
         pipe = emu.EmuPipeline(3)
         for _ in range(2):

@@ -57,8 +57,9 @@ for fv, name in ((1, "voted"), (2, "two_pass")):
 os.environ["RFB_FWD_VARIANT"] = "0"
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res["tape"] = pipe.tape_status()
-# 0 shipped; 1-3 neighbouring cache configurations; 4/5/6 the experimental pooled-row kernel (16/32/8 rows)
-for v in (int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5,6").split(",")):
+# 0 shipped; 1-3 neighbouring cache configurations; 4/5/6 the experimental pooled-row kernel (16/32/8 rows);
+# 7/8 the same with lone lanes reducing directly (16/8 rows)
+for v in (int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5,6,7,8").split(",")):
     os.environ["RFB_BWD_VARIANT"] = str(v)
     out = bwd()
     res[f"replay_v{v}_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
