@@ -1070,7 +1070,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
         const unsigned grp = __match_any_sync(FULL, emit ? emit_cell : (0x80000000u | lane));
         // MIN_GROUP > 1: lanes in groups smaller than that reduce their own complete row directly, all at once (a
         // lone lane is 9 % of the lane-steps but 39 % of the groups, i.e. of the serial rounds)
-        const bool direct = emit && __popc(grp) < MIN_GROUP;
+        const bool direct = MIN_GROUP > 1 && emit && __popc(grp) < MIN_GROUP;
         if (direct) {
             const float4 lo = my_rec[0], hi = my_rec[1];
             float *grow = p.acc + (uint64_t)emit_cell * GR;
