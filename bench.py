@@ -310,17 +310,32 @@ def run_ours(args):
 
     fetch = InputPrefetcher(shard_host, ("rays", "start", "dq", "target"), dev)
 
-    def step_e2e(batch, ev):
+    phase_names = ("enqueue_h2d", "forward_call", "loss_ops", "backward_call", "loss_readback")
+    e2e_phases = []   # per step: host milliseconds spent in each phase
+    e2e_cpu = []      # per step: CPU time of the main thread (a gap to the wall time = descheduled / blocked)
+    e2e_gpu_ev = []   # per step: CUDA events around the step's GPU work
+
+    def step_e2e(batch, ev, ph):
+        t0 = time.perf_counter()
+        e_a = torch.cuda.Event(enable_timing=True)
         torch.cuda.current_stream(dev).wait_event(ev)
+        e_a.record()
         pipe.invalidate_cache()
         pts_p.grad = None
         attrs_p.grad = None
         rgba, depth, _, _ = sharded.ShardedTraceRays.apply(tracer, pts_p, attrs_p, adj, off, batch["rays"],
                                                            batch["start"], batch["dq"], False)
+        t1 = time.perf_counter()
         # train.py:187-204 shape: colour loss + depth-quantile regulariser (sums: shards add up)
         loss = (((rgba - batch["target"]) ** 2).sum() / R_total
                 + 1e-4 * (depth[..., 0] - depth[..., 1]).abs().sum() / R_total)
+        t2 = time.perf_counter()
         loss.backward()
+        e_b = torch.cuda.Event(enable_timing=True)
+        e_b.record()
+        t3 = time.perf_counter()
+        ph[1:4] = [(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3]
+        e2e_gpu_ev.append((e_a, e_b))
         return loss
 
     e2e_step_wall = []
@@ -331,14 +346,25 @@ def run_ours(args):
         nxt = fetch.enqueue(0)
         last = 0.0
         e2e_step_wall.clear()
+        e2e_phases.clear()
+        e2e_cpu.clear()
+        e2e_gpu_ev.clear()
         for i in range(steps):
             t_step = time.perf_counter()
+            c_step = time.thread_time()
+            ph = [0.0] * 5
             batch, ev = nxt
             if i + 1 < steps:
                 nxt = fetch.enqueue(i + 1)
-            last = float(step_e2e(batch, ev).item())  # D2H read of the step's result
+            ph[0] = (time.perf_counter() - t_step) * 1e3
+            loss = step_e2e(batch, ev, ph)
+            t_r = time.perf_counter()
+            last = float(loss.item())  # D2H read of the step's result
+            ph[4] = (time.perf_counter() - t_r) * 1e3
             fetch.release(i)
             e2e_step_wall.append((time.perf_counter() - t_step) * 1e3)
+            e2e_cpu.append((time.thread_time() - c_step) * 1e3)
+            e2e_phases.append(ph)
         return last
 
     # --- warm-up (also gives the work counters)
@@ -383,18 +409,46 @@ def run_ours(args):
     # foam build leaves a large heap) out of the timed region
     gc.collect()
     gc.freeze()
-    gc.disable()
+    if not os.environ.get("RFB_BENCH_GC_ON"):
+        gc.disable()
     barrier(world)
+    mem0 = torch.cuda.memory_stats(dev)
+    lib0 = rp.device_alloc_counts()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss_val = run_e2e(args.steps)
     e1.record()
     barrier(world)
     gc.enable()
+    mem1 = torch.cuda.memory_stats(dev)
+    lib1 = rp.device_alloc_counts()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
     e2e_steps = [round(x, 2) for x in e2e_step_wall]
     h2d = sum(shard_host[k].numel() * shard_host[k].element_size() for k in ("rays", "start", "dq", "target"))
     h2d_ms = fetch.last_copy_ms()
+    wall = np.array(e2e_step_wall)
+    slow = [int(i) for i in np.nonzero(wall > 1.3 * np.median(wall))[0]]
+    ph = np.array(e2e_phases)
+    gpu_ms = np.array([a.elapsed_time(b) for a, b in e2e_gpu_ev])
+    e2e_diag = {
+        "step_wall_ms": {"min": float(wall.min()), "median": float(np.median(wall)), "max": float(wall.max())},
+        "steps_over_1p3x_median": slow,
+        "phase_ms_median": {n: round(float(np.median(ph[:, j])), 3) for j, n in enumerate(phase_names)},
+        "phase_ms_max": {n: round(float(ph[:, j].max()), 3) for j, n in enumerate(phase_names)},
+        "slow_steps": [{"step": i, "wall_ms": round(float(wall[i]), 2), "cpu_ms": round(float(e2e_cpu[i]), 2),
+                        "gpu_ms": round(float(gpu_ms[i]), 2),
+                        "phases": {n: round(float(ph[i, j]), 2) for j, n in enumerate(phase_names)}}
+                       for i in slow[:8]],
+        "gpu_step_ms": {"min": float(gpu_ms.min()), "median": float(np.median(gpu_ms)), "max": float(gpu_ms.max())},
+        "torch_device_allocs": int(mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0)),
+        "torch_device_frees": int(mem1.get("num_device_free", 0) - mem0.get("num_device_free", 0)),
+        "torch_alloc_retries": int(mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0)),
+        "torch_reserved_bytes": int(mem1.get("reserved_bytes.all.current", 0)),
+        "torch_reserved_growth_bytes": int(mem1.get("reserved_bytes.all.current", 0)
+                                           - mem0.get("reserved_bytes.all.current", 0)),
+        "lib_device_allocs": lib1[0] - lib0[0], "lib_device_frees": lib1[1] - lib0[1],
+        "gc": "on" if os.environ.get("RFB_BENCH_GC_ON") else "frozen+disabled",
+    }
 
     if rank != 0:
         return
@@ -434,7 +488,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": R_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "loss": loss_val,
-                "h2d_ms_per_step": h2d_ms, "h2d_overlapped": True, "host_wall_ms_each_step": e2e_steps},
+                "h2d_ms_per_step": h2d_ms, "h2d_overlapped": True, "host_wall_ms_each_step": e2e_steps,
+                "diag": e2e_diag},
         "gpu_launches": int(launches),
         "kernels_ms": {"forward_kernel": k_fwd, "backward_kernel": k_bwd},
         "walk_tape": tape,

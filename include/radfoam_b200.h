@@ -209,6 +209,10 @@ int rfb_trace_benchmark(rfb_pipeline *pipeline, const rfb_trace_settings *settin
 uint64_t rfb_launch_count(void);
 void rfb_reset_launch_count(void);
 
+/* cudaMalloc / cudaFree calls this library has made since it was loaded (its scratch buffers are grow-only:
+ * both stay constant in steady state; bench.py reports the delta over its timed loops) */
+void rfb_device_alloc_counts(uint64_t *allocs, uint64_t *frees);
+
 /* drop cached scene mirrors (next call rebuilds) */
 void rfb_invalidate_cache(rfb_pipeline *pipeline);
 

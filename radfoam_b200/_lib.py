@@ -64,6 +64,7 @@ SIGNATURES = {
                                     POINTER(Camera), _P, _P, POINTER(LaunchOpts), _P]),
     "rfb_launch_count": (c_uint64, []),
     "rfb_reset_launch_count": (None, []),
+    "rfb_device_alloc_counts": (None, [POINTER(c_uint64), POINTER(c_uint64)]),
     "rfb_invalidate_cache": (None, [_P]),
     "rfb_tape_status": (c_int, [_P, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]),
     "rfb_set_profiling": (None, [_P, c_int]),

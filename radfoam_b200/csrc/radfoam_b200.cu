@@ -28,6 +28,7 @@ namespace {
 
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0}; // process-wide: autograd runs backward on its own thread
+std::atomic<uint64_t> g_device_allocs{0}, g_device_frees{0}; // cudaMalloc / cudaFree calls made by this library
 
 int fail(const std::string &msg) {
     g_last_error = msg;
@@ -56,6 +57,7 @@ struct DeviceBuffer {
         if (need <= bytes)
             return cudaSuccess;
         if (ptr) {
+            ++g_device_frees;
             cudaError_t e = cudaFree(ptr);
             ptr = nullptr;
             bytes = 0;
@@ -63,6 +65,7 @@ struct DeviceBuffer {
                 return e;
         }
         size_t want = need + need / 16 + 256;
+        ++g_device_allocs;
         cudaError_t e = cudaMalloc(&ptr, want);
         if (e == cudaSuccess)
             bytes = want;
@@ -433,6 +436,12 @@ const char *rfb_last_error(void) { return g_last_error.c_str(); }
 int rfb_abi_version(void) { return RFB_ABI_VERSION; }
 uint64_t rfb_launch_count(void) { return g_launches.load(); }
 void rfb_reset_launch_count(void) { g_launches.store(0); }
+void rfb_device_alloc_counts(uint64_t *allocs, uint64_t *frees) {
+    if (allocs)
+        *allocs = g_device_allocs.load();
+    if (frees)
+        *frees = g_device_frees.load();
+}
 
 int rfb_create_pipeline(int sh_degree, int attr_dtype, rfb_pipeline **out) {
     if (!out)

@@ -652,3 +652,10 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.load().rfb_reset_launch_count()
+
+
+def device_alloc_counts() -> tuple[int, int]:
+    """(cudaMalloc, cudaFree) calls the native library has made so far (steady state: constant)."""
+    a, f = ctypes.c_uint64(), ctypes.c_uint64()
+    _lib.load().rfb_device_alloc_counts(ctypes.byref(a), ctypes.byref(f))
+    return int(a.value), int(f.value)
