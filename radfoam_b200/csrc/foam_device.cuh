@@ -55,15 +55,6 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 #endif
 }
 
-// 8-byte variant (used by the pooled backward, whose lanes own 6 consecutive floats of a row)
-__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
-#ifdef RFB_EMU
-    rfb_emu_red_add_v2(addr, a, b);
-#else
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-#endif
-}
-
 // ---------------------------------------------------------------- SH basis
 // Real SH basis of the (unit) direction; same formulas and evaluation order as
 // sh_coefficients<deg>() (sh_utils.cuh:34-70) so nvcc contracts them alike.
@@ -128,7 +119,20 @@ __device__ __forceinline__ void sh_to_rgb(const float *__restrict__ row, const f
 struct RayGeom {
     float ox, oy, oz; // origin
     float dx, dy, dz; // unit direction
+    // The ranked face scan flushes subnormals (MUFU.RCP), so a front face whose dp = o.d is a positive
+    // subnormal would drop out of the ranking while the reference still divides by it.  Face offsets are
+    // fp16 values (|o_i| >= 2^-24 or 0), so every nonzero partial sum of dp is a multiple of
+    // 2^-34 * 2^-23 * min|d_i| over the nonzero d_i: with all nonzero |d_i| >= 2^-60 a nonzero dp is
+    // >= 2^-117, never subnormal.  Rays with a smaller nonzero direction component (pathological input)
+    // take the exact scan on every step instead.
+    bool exact_only;
 };
+
+__device__ __forceinline__ bool needs_exact_scan(float dx, float dy, float dz) {
+    const float kTiny = 8.673617379884035e-19f; // 2^-60
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    return (ax != 0.0f && ax < kTiny) || (ay != 0.0f && ay < kTiny) || (az != 0.0f && az < kTiny);
+}
 
 // ray.direction /= ray.direction.norm()  (pipeline.cu:39-40): squared norm in the
 // x0 + (x1 + x2) order with the two fusions nvcc applies, IEEE sqrt and division.
@@ -231,6 +235,10 @@ struct PaddedFaces {
     __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
                                          const RayGeom &ray, float &t1, uint32_t &face) const {
         const float kInf = __int_as_float(0x7f800000);
+        if (ray.exact_only) {
+            scan_exact(begin, nf, px, py, pz, ray, t1, face);
+            return;
+        }
         const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
         float best = kInf, second = kInf; // invariant: best <= second
         uint32_t bf = kNone;
@@ -290,147 +298,6 @@ struct PaddedFaces {
             face = bf;
         } else {
             scan_exact(begin, nf, px, py, pz, ray, t1, face);
-        }
-    }
-    // EXPERIMENT (forward_record_kernel<.., SCAN = 1>, RFB_FWD_VARIANT=1; not the default, not yet measured):
-    // the ranked scan run warp-synchronously -- every lane calls it, `active` false for lanes without a step -- so
-    // that a 4-face chunk in which NO lane has a front face (dp > 0) is skipped after the dp part by a vote.  Such a
-    // chunk only produces q = +inf for every lane, which leaves (best, second, bf) untouched, so the result is the
-    // same.  tests/tools/face_loop_stats.py: 31 % of the warp-level chunk iterations are of that kind.
-    __device__ __forceinline__ void scan_voted(bool active, uint32_t begin, uint32_t nf, float px, float py,
-                                               float pz, const RayGeom &ray, float &t1, uint32_t &face) const {
-        constexpr unsigned FULL = 0xffffffffu;
-        const float kInf = __int_as_float(0x7f800000);
-        const uint32_t my_nf = active ? nf : 0u;
-        const uint32_t max_nf = __reduce_max_sync(FULL, my_nf);
-        const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
-        float best = kInf, second = kInf;
-        uint32_t bf = kNone;
-        for (uint32_t f = 0; f < max_nf; f += 4) {
-            const bool have = f < my_nf;
-            uint2 rec[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
-            float dp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            bool front = false;
-            if (have) {
-                uint4 a = ldg4(p + (f >> 1));
-                uint4 b = ldg4(p + (f >> 1) + 1);
-                rec[0] = make_uint2(a.x, a.y);
-                rec[1] = make_uint2(a.z, a.w);
-                rec[2] = make_uint2(b.x, b.y);
-                rec[3] = make_uint2(b.z, b.w);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
-                    __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
-                    dp[k] = __fmaf_rn(__low2float(hxy), ray.dx,
-                                      __fmaf_rn(__high2float(hxy), ray.dy, __fmul_rn(__low2float(hzw), ray.dz)));
-                    front |= dp[k] > 0.0f;
-                }
-            }
-            const bool needed = __any_sync(FULL, front);
-#ifdef RFB_EMU
-            rfb_emu_count_vote(needed); // statistics on the CPU emulator only
-#endif
-            if (!needed)
-                continue; // no lane can leave through any of these four faces
-            if (have) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float num, dpk;
-                    walk_face_parts(rec[k], px, py, pz, ray, num, dpk); // dpk == dp[k] (same expression)
-                    float q = num * rcp_approx(dpk);
-                    q = (dpk > 0.0f) ? q : kInf;
-                    bf = (q < best) ? f + k : bf;
-                    second = fminf(second, fmaxf(best, q));
-                    best = fminf(best, q);
-                }
-            }
-        }
-        if (!active)
-            return;
-        if (best == kInf) { // as in scan(): hull exit, or a front face whose quotient overflowed
-            bool any_front = false;
-            for (uint32_t f = 0; f < nf; f += 4) {
-                uint4 a = ldg4(p + (f >> 1));
-                uint4 b = ldg4(p + (f >> 1) + 1);
-                uint2 rec[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y),
-                                make_uint2(b.z, b.w)};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
-                    __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
-                    float dp = __fmaf_rn(__low2float(hxy), ray.dx,
-                                         __fmaf_rn(__high2float(hxy), ray.dy,
-                                                   __fmul_rn(__low2float(hzw), ray.dz)));
-                    any_front |= dp > 0.0f;
-                }
-            }
-            if (!any_front)
-                return;
-            scan_exact(begin, nf, px, py, pz, ray, t1, face);
-            return;
-        }
-        float ab = fabsf(best);
-        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
-        bool clear = (second - best) > margin;
-        if (clear && fabsf(best) < 1e30f) {
-            float t, dp;
-            walk_face(ldg2(faces + begin + bf), px, py, pz, ray, t, dp);
-            t1 = t;
-            face = bf;
-        } else {
-            scan_exact(begin, nf, px, py, pz, ray, t1, face);
-        }
-    }
-    // EXPERIMENT (RFB_FWD_VARIANT=2; not the default, not yet measured): two passes per lane.  Pass 1 computes only
-    // dp of every face (6 of the ~25 instructions per face) and collects the front faces (dp > 0, 46 % of all) in a
-    // bit mask; pass 2 ranks just those, in ascending face order so that "first minimum wins" is preserved.  Rows
-    // longer than 64 faces fall back to scan().  Fewer instructions, more (L1-resident) 8-byte loads.
-    __device__ __forceinline__ void scan_two_pass(uint32_t begin, uint32_t nf, float px, float py, float pz,
-                                                  const RayGeom &ray, float &t1, uint32_t &face) const {
-        if (nf > 64u) {
-            scan(begin, nf, px, py, pz, ray, t1, face);
-            return;
-        }
-        const float kInf = __int_as_float(0x7f800000);
-        const uint4 *p = reinterpret_cast<const uint4 *>(faces + begin);
-        unsigned long long front = 0ull;
-        for (uint32_t f = 0; f < nf; f += 4) {
-            uint4 a = ldg4(p + (f >> 1));
-            uint4 b = ldg4(p + (f >> 1) + 1);
-            uint2 rec[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y), make_uint2(b.z, b.w)};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                __half2 hxy = *reinterpret_cast<__half2 *>(&rec[k].x);
-                __half2 hzw = *reinterpret_cast<__half2 *>(&rec[k].y);
-                float dp = __fmaf_rn(__low2float(hxy), ray.dx,
-                                     __fmaf_rn(__high2float(hxy), ray.dy, __fmul_rn(__low2float(hzw), ray.dz)));
-                front |= (unsigned long long)(dp > 0.0f) << (f + k);
-            }
-        }
-        if (front == 0ull)
-            return; // no face with dp > 0: the reference finds none either (hull exit)
-        float best = kInf, second = kInf;
-        uint32_t bf = kNone;
-        for (unsigned long long m = front; m; m &= m - 1) {
-            const uint32_t f = (uint32_t)__ffsll((long long)m) - 1u;
-            float num, dp;
-            walk_face_parts(ldg2(faces + begin + f), px, py, pz, ray, num, dp);
-            float q = num * rcp_approx(dp); // dp > 0 here
-            bf = (q < best) ? f : bf;
-            second = fminf(second, fmaxf(best, q));
-            best = fminf(best, q);
-        }
-        float ab = fabsf(best);
-        float margin = 1.9073486e-06f * fmaxf(ab, fminf(fabsf(second), 4.0f * ab + 1e-30f)) + 1e-35f;
-        bool clear = (second - best) > margin;
-        if (best != kInf && clear && fabsf(best) < 1e30f) {
-            float t, dp;
-            walk_face(ldg2(faces + begin + bf), px, py, pz, ray, t, dp);
-            t1 = t;
-            face = bf;
-        } else {
-            scan_exact(begin, nf, px, py, pz, ray, t1, face); // near-tie, overflow, NaN: literally the reference's loop
         }
     }
     __device__ __forceinline__ uint32_t neighbour(uint32_t begin, uint32_t face) const {

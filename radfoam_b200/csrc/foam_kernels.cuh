@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ForwardParams p, 
         ray.dy = __ldg(rp + 4);
         ray.dz = __ldg(rp + 5);
         normalize_dir(ray.dx, ray.dy, ray.dz);
+        ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
     }
     float sh[sh_dim(DEG)];
     sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
@@ -240,7 +241,7 @@ struct Tape {
 // Forward with an explicit warp-synchronous loop (all lanes stay in the loop until the warp is
 // done, so lane 0 can allocate tape chunks for the warp) that records the tape.
 template <int DEG, typename Faces>
-__global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
+__global__ void __launch_bounds__(kBlock, 7) forward_record_kernel(const ForwardParams p, const Faces fa,
                                                                 const Tape tape) {
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardPar
     bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
     const bool has_ray = !done;
 
-    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, false};
     float sh[sh_dim(DEG)];
     uint32_t Q = 0, qi = 0;
     const float *qv = nullptr;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardPar
         ray.dy = __ldg(rp + 4);
         ray.dz = __ldg(rp + 5);
         normalize_dir(ray.dx, ray.dy, ray.dz);
+        ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
         Q = p.quantiles ? p.num_q : 0u;
         qv = p.quantiles + (uint64_t)r * p.num_q;
         cq = Q ? __ldg(qv) : 0.0f;
@@ -368,149 +370,6 @@ __global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardPar
         p.nint[r] = n;
 }
 
-// EXPERIMENTS (RFB_FWD_VARIANT=1 / 2; not the default, not yet measured on a B200): forward_record_kernel with
-//   SCAN == 1  the face scan run warp-synchronously so that 4-face chunks without a front face for any lane are skipped
-//              by a vote (PaddedFaces::scan_voted);
-//   SCAN == 2  the two-pass scan (PaddedFaces::scan_two_pass): dp of all faces first, ranking of the front faces only.
-// Everything else is a copy of the kernel above; results are identical (tests/test_emu_kernels.py).
-template <int DEG, typename Faces, int SCAN>
-__global__ void __launch_bounds__(kBlock) forward_record_voted_kernel(const ForwardParams p, const Faces fa,
-                                                                const Tape tape) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-    uint32_t r;
-    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
-    const bool has_ray = !done;
-
-    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-    float sh[sh_dim(DEG)];
-    uint32_t Q = 0, qi = 0;
-    const float *qv = nullptr;
-    float cq = 0.0f;
-    uint32_t cur = 0;
-    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_ray) {
-        const float *rp = p.rays + 6 * (uint64_t)r;
-        ray.ox = __ldg(rp + 0);
-        ray.oy = __ldg(rp + 1);
-        ray.oz = __ldg(rp + 2);
-        ray.dx = __ldg(rp + 3);
-        ray.dy = __ldg(rp + 4);
-        ray.dz = __ldg(rp + 5);
-        normalize_dir(ray.dx, ray.dy, ray.dz);
-        Q = p.quantiles ? p.num_q : 0u;
-        qv = p.quantiles + (uint64_t)r * p.num_q;
-        cq = Q ? __ldg(qv) : 0.0f;
-        cur = __ldg(p.start + r);
-        pc = ldg4(p.cells + cur);
-    }
-    sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
-
-    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, t0 = 0.0f;
-    uint32_t n = 0, nrec = 0;
-    uint32_t chunk = kTapeNoChunk;
-    for (uint32_t k = 0;; ++k) {
-        if ((k % kTapeChunk) == 0) { // the warp enters a new chunk of steps
-            uint32_t c = kTapeNoChunk;
-            if (lane == 0) {
-                c = atomicAdd(tape.ctrl, 1u);
-                if (c >= tape.capacity || k / kTapeChunk >= tape.table_stride) {
-                    atomicExch(tape.ctrl + 1, 1u);
-                    c = kTapeNoChunk;
-                } else {
-                    tape.table[(uint64_t)gwarp * tape.table_stride + k / kTapeChunk] = c;
-                }
-            }
-            chunk = __shfl_sync(FULL, c, 0);
-        }
-        // the face scan, hoisted out of the divergent region and run by the whole warp
-        bool stepping = !done;
-        uint32_t v_begin = 0, v_nf = 0, v_face = kNone;
-        float v_t1 = __int_as_float(0x7f800000);
-        if (stepping && n + 1 > p.max_steps)
-            stepping = false; // the budget check below ends the ray
-        if (stepping)
-            fa.row(cur, v_begin, v_nf);
-        if (SCAN == 1)
-            fa.scan_voted(stepping, v_begin, v_nf, pc.x, pc.y, pc.z, ray, v_t1, v_face);
-        else if (stepping)
-            fa.scan_two_pass(v_begin, v_nf, pc.x, pc.y, pc.z, ray, v_t1, v_face);
-        if (!done) {
-            n++;
-            if (n > p.max_steps) {
-                done = true;
-            } else {
-                const uint32_t begin = v_begin, face = v_face;
-                const float t1 = v_t1;
-                if (face == kNone) {
-                    done = true;
-                } else {
-                    if (chunk != kTapeNoChunk) // streaming store: the tape is written once, read once
-                        __stcs(tape.pool + ((uint64_t)chunk * kTapeChunk + (k % kTapeChunk)) * 32 + lane,
-                               make_uint2(cur, __float_as_uint(t1)));
-                    nrec++;
-                    uint32_t nxt = fa.neighbour(begin, face);
-                    float4 pn = ldg4(p.cells + nxt);
-                    if (t1 > t0) {
-                        float s = pc.w;
-                        float r_ = 0.0f, g_ = 0.0f, b_ = 0.0f;
-                        if (s > 1e-6f)
-                            sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * sh_row(DEG), sh, r_, g_, b_);
-                        float delta = fmaxf(__fsub_rn(t1, t0), 0.0f);
-                        float alpha = 1.0f - expf(-s * delta);
-                        float w = __fmul_rn(T, alpha);
-                        if (p.contrib) {
-                            if (p.out_half)
-                                atomicAdd(reinterpret_cast<__half *>(p.contrib) + cur, __float2half_rn(w));
-                            else
-                                atomicAdd(reinterpret_cast<float *>(p.contrib) + cur, w);
-                        }
-                        cr = __fmaf_rn(w, r_, cr);
-                        cg = __fmaf_rn(w, g_, cg);
-                        cb = __fmaf_rn(w, b_, cb);
-                        float Tn = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                        while (qi < Q && Tn < cq) {
-                            p.qdepth[(uint64_t)r * Q + qi] = __fadd_rn(t0, __fdiv_rn(logf(__fdiv_rn(T, cq)), s));
-                            p.qidx[(uint64_t)r * Q + qi] = cur;
-                            qi++;
-                            if (qi < Q)
-                                cq = __ldg(qv + qi);
-                        }
-                        T = Tn;
-                        done = !(T > p.weight_threshold);
-                    }
-                    t0 = fmaxf(t0, t1);
-                    cur = nxt;
-                    pc = pn;
-                }
-            }
-        }
-        if (!__any_sync(FULL, !done))
-            break;
-    }
-    if (!has_ray)
-        return;
-    tape.per_ray[r] = make_uint2(nrec, cur);
-    while (qi < Q) {
-        p.qdepth[(uint64_t)r * Q + qi] = -1.0f;
-        p.qidx[(uint64_t)r * Q + qi] = kNone;
-        qi++;
-    }
-    float a = __fsub_rn(1.0f, T);
-    if (p.out_half) {
-        __half2 lo = __floats2half2_rn(cr, cg), hi = __floats2half2_rn(cb, a);
-        uint2 v;
-        v.x = *reinterpret_cast<uint32_t *>(&lo);
-        v.y = *reinterpret_cast<uint32_t *>(&hi);
-        reinterpret_cast<uint2 *>(p.rgba)[r] = v;
-    } else {
-        reinterpret_cast<float4 *>(p.rgba)[r] = make_float4(cr, cg, cb, a);
-    }
-    if (p.nint)
-        p.nint[r] = n;
-}
-
 // ------------------------------------------------------------------ backward
 struct BackwardParams {
     const float4 *cells;
@@ -546,6 +405,7 @@ __device__ __forceinline__ void backward_ray_setup(const BackwardParams &p, uint
     ray.dy = __ldg(rp + 4);
     ray.dz = __ldg(rp + 5);
     normalize_dir(ray.dx, ray.dy, ray.dz);
+        ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
     sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
     st.err = 0.0f;
     if (p.io_half) {
@@ -690,7 +550,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 
     uint32_t r;
     bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
-    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, false};
     float sh[sh_dim(DEG)];
     BackwardRay st;
     uint32_t cur = 0;
@@ -888,344 +748,6 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
     }
 }
 
-// ---- backward, pooled rows (EXPERIMENT, not the default: RFB_BWD_VARIANT=4..6; functionally checked on the CPU
-// emulator, tests/test_emu_kernels.py, not yet measured on a B200)
-// tests/tools/tape_stats.py on a scene with the bench's rays/points ratio: 40 % of the composited lane-steps sit in
-// same-cell groups of fewer than 6 lanes, which the kernel above reduces directly and which produce 78 % of its
-// 16-byte reductions; another 15 % are the per-step position-gradient reductions.  A 16-row cache fed by EVERY group
-// would issue 0.29x the reductions (32 rows: 0.22x) -- but only if a group costs far less than one serial warp round.
-// This kernel changes three things:
-//  * a lane's record is compact: (dL/drgb, dL/dsigma | position gradient) = 32 bytes in shared memory, plus the
-//    ray's SH basis (64 bytes, written once).  The row is rank one in (basis x dL/drgb), so it is expanded while it is
-//    summed instead of being staged as 52 floats;
-//  * the record of cell i is completed by the position gradient that the walk hands over one composited cell later
-//    (quirk A.5.1) and only then routed, so position gradients ride in the row (floats 49..51) instead of costing a
-//    reduction of their own; the last cell's record leaves with a zero position gradient, as upstream never flushes it;
-//  * groups are summed by QUARTER warps, four groups per round: lane `sub` of a quarter owns SH coefficients
-//    k = 2 sub, 2 sub + 1 (6 floats), lane 0 also the 4 trailing floats.  A group of >= 16 lanes takes a round of its
-//    own: it is split over the four quarters by lane range and the partial rows are combined by shuffles.  Every
-//    group goes through the warp's row cache (SLOTS rows, direct-mapped); two groups of one round that hash to the
-//    same row are not scheduled together.  The round scheduler reads the groups from a list the leaders publish in
-//    shared memory (no shuffles).  With MIN_GROUP = 2 lone lanes bypass all that and reduce their row directly.
-template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS, bool REPLAY>
-__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
-    backward_pooled_kernel(const BackwardParams p, const Faces fa, const Tape tape) {
-    if (tape.pool != nullptr) {
-        const bool overflowed = tape.ctrl[1] != 0u;
-        if (REPLAY == overflowed)
-            return;
-    }
-    constexpr int GR = grad_row(DEG);
-    constexpr int SR = sh_row(DEG);
-    constexpr int NK = sh_dim(DEG);
-    constexpr unsigned FULL = 0xffffffffu;
-    static_assert(DEG == 3, "lane ownership (6 floats per lane, 8 lanes) is laid out for 16 SH coefficients");
-    static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS <= 32, "SLOTS: power of two, at most 32");
-
-#ifdef RFB_EMU
-    float *smem = rfb_emu_dynamic_smem();
-#else
-    extern __shared__ __align__(16) float smem[];
-#endif
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, quarter = lane >> 3;
-    constexpr int WARP_FLOATS = 32 * 8 + 32 * 16 + SLOTS * GR + 128 + SLOTS;
-    float *rec = smem + warp * WARP_FLOATS;                              // [32][8]  (g0 g1 g2 ds | gx gy gz 0)
-    float *bas = rec + 32 * 8;                                           // [32][16] SH basis of the lane's ray
-    float *cache = bas + 32 * 16;                                        // [SLOTS][GR]
-    uint4 *glist = reinterpret_cast<uint4 *>(cache + SLOTS * GR);        // [32] this iteration's groups
-    uint32_t *tags = reinterpret_cast<uint32_t *>(glist + 32);           // [SLOTS]
-    for (int i = lane; i < SLOTS; i += 32)
-        tags[i] = kNone;
-
-    uint32_t r;
-    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
-    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-    float sh[NK];
-    BackwardRay st;
-    uint32_t cur = 0;
-    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + warp;
-    uint32_t nrec = 0, last_cell = 0;
-    uint2 rec_a = make_uint2(0u, 0u);
-    if (!done) {
-        backward_ray_setup<DEG>(p, r, ray, sh, st);
-        cur = __ldg(p.start + r);
-        pc = ldg4(p.cells + cur);
-        if (REPLAY) {
-            uint2 pr = tape.per_ray[r];
-            nrec = pr.x;
-            last_cell = pr.y;
-            done = nrec == 0;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < NK; ++i)
-            sh[i] = 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        bas[lane * 16 + i] = i < NK ? sh[i] : 0.0f;
-    __syncwarp();
-
-    float t0 = 0.0f;
-    uint32_t n = 0;
-    uint32_t chunk_ahead = 0;
-    uint2 rec_b = make_uint2(0u, 0u);
-    auto tape_row = [&](uint32_t chunk_id, uint32_t j) -> uint2 {
-        return j < nrec ? __ldcs(tape.pool + ((uint64_t)chunk_id * kTapeChunk + (j % kTapeChunk)) * 32 + lane)
-                        : make_uint2(last_cell, 0u);
-    };
-    if (REPLAY) {
-        chunk_ahead = tape.table[(uint64_t)gwarp * tape.table_stride];
-        if (!done) {
-            rec_a = tape_row(chunk_ahead, 0);
-            rec_b = tape_row(chunk_ahead, 1);
-        }
-    }
-    uint32_t pend_cell = kNone; // cell of the record waiting in rec[lane] for its position gradient
-    float4 *my_rec = reinterpret_cast<float4 *>(rec + lane * 8);
-    const float4 *rec4 = reinterpret_cast<const float4 *>(rec);
-    const float2 *bas2 = reinterpret_cast<const float2 *>(bas);
-
-    for (uint32_t k = 0;; ++k) {
-        bool c_valid = false;
-        float dL_ds = 0.0f;
-        float dL_drgb[3] = {0.0f, 0.0f, 0.0f};
-        uint32_t new_cell = kNone;
-        bool emit = false;
-        uint32_t emit_cell = kNone;
-
-        bool step = false;
-        float t1 = __int_as_float(0x7f800000);
-        uint32_t nxt = 0;
-        if (REPLAY) {
-            if (((k + 2) % kTapeChunk) == 0)
-                chunk_ahead = tape.table[(uint64_t)gwarp * tape.table_stride + (k + 2) / kTapeChunk];
-            if (!done) {
-                uint2 rec_c = tape_row(chunk_ahead, k + 2);
-                t1 = __uint_as_float(rec_a.y);
-                nxt = rec_b.x;
-                rec_a = rec_b;
-                rec_b = rec_c;
-                step = true;
-            }
-        } else if (!done) {
-            n++;
-            if (n > p.max_steps) {
-                done = true;
-            } else {
-                uint32_t begin, nf;
-                fa.row(cur, begin, nf);
-                uint32_t face = kNone;
-                fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
-                if (face == kNone) {
-                    done = true;
-                } else {
-                    nxt = fa.neighbour(begin, face);
-                    step = true;
-                }
-            }
-        }
-        if (step) {
-            float4 pn = ldg4(p.cells + nxt);
-            if (t1 > t0) {
-                float rgb[3] = {0.0f, 0.0f, 0.0f};
-                if (pc.w > 1e-6f)
-                    sh_to_rgb<DEG>(p.sh_rows + (uint64_t)cur * SR, sh, rgb[0], rgb[1], rgb[2]);
-                float w, fx, fy, fz;
-                bool flush;
-                uint32_t flush_idx;
-                bool go = st.cell(cur, pc, pn, t0, t1, rgb, ray, p.weight_threshold, dL_drgb, dL_ds, w, flush,
-                                  flush_idx, fx, fy, fz);
-                if (p.point_error)
-                    add_point_error(p, cur, __fmul_rn(w, st.err));
-                if (flush) { // flush_idx == pend_cell: the waiting record is complete now
-#ifdef RFB_EMU
-                    if (flush_idx != pend_cell)
-                        __builtin_trap(); // invariant of the record pipeline, checked on the CPU emulator only
-#endif
-                    my_rec[1] = make_float4(fx, fy, fz, 0.0f);
-                    emit = true;
-                    emit_cell = pend_cell;
-                }
-                c_valid = true;
-                new_cell = cur;
-                done = !go;
-            }
-            t0 = fmaxf(t0, t1);
-            cur = nxt;
-            pc = pn;
-            if (REPLAY && k + 1 >= nrec)
-                done = true;
-        } else if (pend_cell != kNone) {
-            // the ray has ended: its last record leaves without a position gradient (never flushed upstream)
-            my_rec[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            emit = true;
-            emit_cell = pend_cell;
-            pend_cell = kNone;
-        }
-        __syncwarp();
-
-        // ---- warp-collective phase: sum the complete records by cell, four groups per round
-        const unsigned grp = __match_any_sync(FULL, emit ? emit_cell : (0x80000000u | lane));
-        // MIN_GROUP > 1: lanes in groups smaller than that reduce their own complete row directly, all at once (a
-        // lone lane is 9 % of the lane-steps but 39 % of the groups, i.e. of the serial rounds)
-        const bool direct = MIN_GROUP > 1 && emit && __popc(grp) < MIN_GROUP;
-        if (direct) {
-            const float4 lo = my_rec[0], hi = my_rec[1];
-            float *grow = p.acc + (uint64_t)emit_cell * GR;
-            if (lo.x != 0.0f || lo.y != 0.0f || lo.z != 0.0f) {
-#pragma unroll
-                for (int i = 0; i < SR; i += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int e = i + j, c = e % 3;
-                        v[j] = e < 3 * NK ? __fmul_rn(sh[e / 3], c == 0 ? lo.x : (c == 1 ? lo.y : lo.z)) : 0.0f;
-                    }
-                    red_add_v4(grow + i, v[0], v[1], v[2], v[3]);
-                }
-            }
-            red_add_v4(grow + SR, lo.w, hi.x, hi.y, hi.z);
-        }
-        const bool is_leader = emit && !direct && (uint32_t)(__ffs(grp) - 1) == lane;
-        const unsigned leaders = __ballot_sync(FULL, is_leader);
-        if (leaders == 0u) {
-            // nothing to route in this iteration
-        } else {
-            // the leaders publish (lane mask, cell) in lane order so that the round scheduler reads them from shared
-            // memory instead of shuffling them
-            if (is_leader) // (lane mask, cell, cache row, lanes): everything the scheduler needs, computed once
-                glist[__popc(leaders & ((1u << lane) - 1u))] =
-                    make_uint4(grp, emit_cell, (emit_cell * 2654435761u) >> (32 - __builtin_ctz(SLOTS)),
-                               (uint32_t)__popc(grp));
-            __syncwarp();
-        }
-        const int num_groups = __popc(leaders);
-        int next_group = 0;
-        while (next_group < num_groups) {
-            unsigned my_members = 0, used = 0;
-            uint32_t my_cell = kNone, my_slot = 0;
-            bool my_owner = false, split = false;
-            int q_next = 0;
-            while (next_group < num_groups && q_next < 4) {
-                const uint4 g = glist[next_group];
-                const unsigned gmask = g.x;
-                const uint32_t cell = g.y, slot = g.z;
-                const bool big = g.w >= 16u; // split over the four quarters by lane range
-                if ((big && q_next != 0) || ((used >> slot) & 1u))
-                    break; // next round (the first candidate of a round always fits)
-                used |= 1u << slot;
-                if (big) {
-                    my_members = gmask & (0xFFu << (8 * quarter));
-                    my_cell = cell;
-                    my_slot = slot;
-                    my_owner = quarter == 0;
-                    split = true;
-                    q_next = 4;
-                } else {
-                    if ((int)quarter == q_next) {
-                        my_members = gmask;
-                        my_cell = cell;
-                        my_slot = slot;
-                        my_owner = true;
-                    }
-                    q_next++;
-                }
-                next_group++;
-            }
-            float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
-            for (unsigned mm = my_members; mm; mm &= mm - 1) {
-                // (two members per trip was tried: +12 live registers -> 48-72 bytes of spill at 5 CTAs/SM)
-                const int m = __ffs(mm) - 1;
-                const float4 lo = rec4[2 * m], hi = rec4[2 * m + 1];
-                const float2 b = bas2[m * 8 + sub];
-                a[0] = __fmaf_rn(b.x, lo.x, a[0]);
-                a[1] = __fmaf_rn(b.x, lo.y, a[1]);
-                a[2] = __fmaf_rn(b.x, lo.z, a[2]);
-                a[3] = __fmaf_rn(b.y, lo.x, a[3]);
-                a[4] = __fmaf_rn(b.y, lo.y, a[4]);
-                a[5] = __fmaf_rn(b.y, lo.z, a[5]);
-                x[0] += lo.w;
-                x[1] += hi.x;
-                x[2] += hi.y;
-                x[3] += hi.z;
-            }
-            if (split) { // partial rows of the four quarters
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    a[i] += __shfl_xor_sync(FULL, a[i], 8);
-                    a[i] += __shfl_xor_sync(FULL, a[i], 16);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    x[i] += __shfl_xor_sync(FULL, x[i], 8);
-                    x[i] += __shfl_xor_sync(FULL, x[i], 16);
-                }
-            }
-            // cache update by the owning quarter; lane `sub` holds floats [6 sub, 6 sub + 6), lane 0 also [SR, SR + 4).
-            // A row that has to make room leaves as 13 x 16-byte reductions (the quarter's lanes take float4 i and
-            // i + 8): same sectors per row as the kernel above, not 3 x 8 bytes per lane.
-            const bool update = my_owner && my_cell != kNone;
-            uint32_t tag = kNone;
-            float *crow = cache + my_slot * GR;
-            if (update)
-                tag = tags[my_slot];
-            const bool hit = tag == my_cell;
-            if (update && !hit && tag != kNone) {
-                float *grow = p.acc + (uint64_t)tag * GR;
-                for (int i = (int)sub; i < GR / 4; i += 8) {
-                    const float4 v = *reinterpret_cast<const float4 *>(crow + 4 * i);
-                    red_add_v4(grow + 4 * i, v.x, v.y, v.z, v.w);
-                }
-            }
-            __syncwarp(); // the old row and its tag have been read
-            if (update) {
-                float2 *mine = reinterpret_cast<float2 *>(crow + 6 * sub); // 8-byte aligned: rows are 208 bytes
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    float2 v = hit ? mine[i] : make_float2(0.0f, 0.0f);
-                    v.x += a[2 * i];
-                    v.y += a[2 * i + 1];
-                    mine[i] = v;
-                }
-                if (sub == 0) {
-                    float4 *tail = reinterpret_cast<float4 *>(crow + SR);
-                    float4 v = hit ? *tail : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    v.x += x[0];
-                    v.y += x[1];
-                    v.z += x[2];
-                    v.w += x[3];
-                    *tail = v;
-                    tags[my_slot] = my_cell;
-                }
-            }
-            __syncwarp();
-        }
-        // the step's own record starts waiting (after the phase above has read the slot)
-        if (c_valid) {
-            my_rec[0] = make_float4(dL_drgb[0], dL_drgb[1], dL_drgb[2], dL_ds);
-            pend_cell = new_cell;
-        }
-        if (!__any_sync(FULL, !done || pend_cell != kNone))
-            break;
-    }
-
-    // drain the cache: quarter q writes rows q, q + 4, ...
-    __syncwarp();
-    for (int slot = (int)quarter; slot < SLOTS; slot += 4) {
-        const uint32_t tag = tags[slot];
-        if (tag == kNone)
-            continue;
-        const float *crow = cache + slot * GR;
-        float *grow = p.acc + (uint64_t)tag * GR;
-        for (int i = (int)sub; i < GR / 4; i += 8) {
-            const float4 v = *reinterpret_cast<const float4 *>(crow + 4 * i);
-            red_add_v4(grow + 4 * i, v.x, v.y, v.z, v.w);
-        }
-    }
-}
-
 // accumulator -> reference-layout gradient outputs (+ optional finite scrub)
 template <typename AttrT>
 __global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t num_points,
@@ -1307,114 +829,48 @@ __global__ void __launch_bounds__(256) nearest_point_kernel(const float *__restr
 
 // ------------------------------------------------------------------ farthest neighbour
 // Per cell: the adjacent point farthest from it and half the mean neighbour distance ("cell radius"),
-// what the densification pass reads (scene.py:434-461; reference kernel triangulation_ops.cu:9-44, one
-// thread per point walking its row with dependent gathers of three scalar loads each).
+// what the densification pass reads (scene.py:434-461; reference kernel triangulation_ops.cu:9-44).
 // Arithmetic as the reference's SASS has it: d = q - p, |d|^2 = fma(dx,dx, fma(dy,dy, dz*dz)), IEEE sqrt and
 // divide, strict '>' first-max from 0, and `sum += 0.5 * dist` evaluated in fp64 and rounded back to fp32 every
 // iteration.  That last step needs no fp64: 0.5*dist is exact and rounding an exact sum to 53 then to 24 bits
 // equals rounding it to 24 bits directly whenever 53 >= 2*24 + 2 (double rounding is innocuous for +), so
-// fmaf(dist, 0.5f, sum) is bit-identical; the FP64CHAIN variants keep the literal form.
-constexpr uint32_t kRowLanes = 8;
-
-struct PackedPoints { // the caller's [N][3] array: three scalar loads per point
-    const float *p;
-    __device__ __forceinline__ float3 operator[](uint64_t i) const {
-        return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
-    }
-};
-struct PaddedPoints { // a float4 mirror: one 16-byte load per point
-    const float4 *p;
-    __device__ __forceinline__ float3 operator[](uint64_t i) const {
-        const float4 v = __ldg(p + i);
-        return make_float3(v.x, v.y, v.z);
-    }
-};
-
-__global__ void __launch_bounds__(256) pad_points_kernel(const float *__restrict__ points, uint32_t num_points,
-                                                         float4 *__restrict__ out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < num_points)
-        out[i] = make_float4(points[3 * i], points[3 * i + 1], points[3 * i + 2], 0.0f);
-}
-
-__device__ __forceinline__ float neighbour_distance(float3 q, float3 p) {
-    const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y), dz = __fsub_rn(q.z, p.z);
+// fmaf(dist, 0.5f, sum) is bit-identical and frees the kernel from the F2F/DFMA pipe the reference's form binds
+// on.  Shape: one thread per row, four faces in flight.  Measured at 1 M points / 15.1 M edges, L2 flushed
+// (profiles/r02_farthest_neighbor.json): this 0.0767 ms, the reference's kernel 0.0870 ms; the alternatives that
+// were built and dropped: 8 lanes per row with the serial chain replayed by shuffle 0.126 ms (fp64 chain 0.161),
+// the same over a float4 point mirror 0.135 ms, thread per row over the mirror 0.080 ms (+ the mirror pass).
+__device__ __forceinline__ float neighbour_distance(const float *__restrict__ points, uint64_t j, float px,
+                                                    float py, float pz) {
+    const float dx = __fsub_rn(points[3 * j], px), dy = __fsub_rn(points[3 * j + 1], py),
+                dz = __fsub_rn(points[3 * j + 2], pz);
     return __fsqrt_rn(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))));
 }
 
-template <bool FP64CHAIN>
-__device__ __forceinline__ float half_distance_sum(float sum, float dist) {
-    if (FP64CHAIN)
-        return __double2float_rn(__fma_rn((double)dist, 0.5, (double)sum));
-    return __fmaf_rn(dist, 0.5f, sum);
-}
-
-// 8 lanes share a row: the adjacency read is one 32-byte sector and the 8 neighbour gathers are in flight
-// together; the reference's in-order accumulation is then replayed over the 8 distances by shuffle.
-template <typename Points, bool FP64CHAIN>
-__global__ void __launch_bounds__(256) farthest_neighbor_kernel(Points points,
+__global__ void __launch_bounds__(256) farthest_neighbor_kernel(const float *__restrict__ points,
                                                                 const uint32_t *__restrict__ adjacency,
                                                                 const uint32_t *__restrict__ offsets,
                                                                 uint32_t num_points,
                                                                 uint32_t *__restrict__ indices,
                                                                 float *__restrict__ cell_radius) {
-    const uint32_t lane = threadIdx.x & 31u, sub = lane & (kRowLanes - 1u);
-    const uint32_t group_mask = 0xffu << (lane & ~(kRowLanes - 1u));
-    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes;
-    if (i >= num_points) // the 8 lanes of a row leave together
-        return;
-    const float3 p = points[i];
-    const uint32_t begin = offsets[i], num_faces = offsets[i + 1] - begin;
-    float sum = 0.0f, farthest = 0.0f;
-    uint32_t farthest_face = kNone;
-    for (uint32_t f0 = 0; f0 < num_faces; f0 += kRowLanes) {
-        const uint32_t f = f0 + sub;
-        float dist = 0.0f;
-        if (f < num_faces)
-            dist = neighbour_distance(points[adjacency[begin + f]], p);
-        const uint32_t count = min(kRowLanes, num_faces - f0);
-        for (uint32_t k = 0; k < count; ++k) { // every lane of the row replays the same sequence
-            const float dk = __shfl_sync(group_mask, dist, k, kRowLanes);
-            sum = half_distance_sum<FP64CHAIN>(sum, dk);
-            if (dk > farthest) {
-                farthest = dk;
-                farthest_face = f0 + k;
-            }
-        }
-    }
-    if (sub == 0) {
-        indices[i] = farthest_face == kNone ? kNone : adjacency[begin + farthest_face];
-        cell_radius[i] = __fdiv_rn(sum, __uint2float_rn(num_faces)); // 0/0 = NaN for an empty row, as upstream
-    }
-}
-
-// One thread per row (the reference's shape), for comparison: fewer instructions per face, scattered reads.
-template <typename Points, bool FP64CHAIN>
-__global__ void __launch_bounds__(256) farthest_neighbor_rows_kernel(Points points,
-                                                                     const uint32_t *__restrict__ adjacency,
-                                                                     const uint32_t *__restrict__ offsets,
-                                                                     uint32_t num_points,
-                                                                     uint32_t *__restrict__ indices,
-                                                                     float *__restrict__ cell_radius) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_points)
         return;
-    const float3 p = points[i];
+    const float px = points[3 * i], py = points[3 * i + 1], pz = points[3 * i + 2];
     const uint32_t begin = offsets[i], num_faces = offsets[i + 1] - begin;
     float sum = 0.0f, farthest = 0.0f;
     uint32_t farthest_idx = kNone;
 #pragma unroll 4
     for (uint32_t f = 0; f < num_faces; ++f) {
         const uint32_t j = adjacency[begin + f];
-        const float dist = neighbour_distance(points[j], p);
-        sum = half_distance_sum<FP64CHAIN>(sum, dist);
+        const float dist = neighbour_distance(points, j, px, py, pz);
+        sum = __fmaf_rn(dist, 0.5f, sum);
         if (dist > farthest) {
             farthest = dist;
             farthest_idx = j;
         }
     }
     indices[i] = farthest_idx;
-    cell_radius[i] = __fdiv_rn(sum, __uint2float_rn(num_faces));
+    cell_radius[i] = __fdiv_rn(sum, __uint2float_rn(num_faces)); // 0/0 = NaN for an empty row, as upstream
 }
 
 // ------------------------------------------------------------------ benchmark
@@ -1425,31 +881,42 @@ struct CameraParams {
     int model;
 };
 
-// cast_ray (camera.h:56-85)
+// cast_ray (camera.h:56-85).  The packed RGBA8 output is held to byte equality with the reference's kernel, so
+// the arithmetic is pinned to the association of its sm_100 SASS (cuobjdump of oracle/_ref, benchmark<float,0>):
+//   aspect = w / h, x = i / w, y = j / h                       IEEE divisions
+//   u = fma(x, 2, -1) * aspect;  v = 1 - (y + y)
+//   pinhole: s = 1 / tanf(fov * 0.5);  d_k = fma(v, up_k, fma(s, forward_k, u * right_k))
+//   fisheye: theta = atan2f(v, u);  phi = sqrtf(fma(u, u, v * v)) * fov, clamped to pi - 1e-6 with mask 0;
+//            a = sinf(phi) * cosf(theta), b = sinf(phi) * sinf(theta)
+//            d_k = fma(cosf(phi), forward_k, fma(b, up_k, a * right_k))
+//   d /= sqrtf(fma(d0, d0, fma(d1, d1, d2 * d2)))  when that is > 0;  d *= mask
+// tanf / atan2f / sinf / cosf are the same libdevice routines the reference calls.
 __device__ __forceinline__ void cast_ray(const CameraParams &c, int i, int j, RayGeom &ray) {
-    float aspect = (float)c.width / (float)c.height;
-    float x = (float)i / (float)c.width;
-    float y = (float)j / (float)c.height;
-    float u = (2.0f * x - 1.0f) * aspect;
-    float v = (1.0f - 2.0f * y);
+    const float aspect = __fdiv_rn((float)c.width, (float)c.height);
+    const float x = __fdiv_rn((float)i, (float)c.width);
+    const float y = __fdiv_rn((float)j, (float)c.height);
+    const float u = __fmul_rn(__fmaf_rn(x, 2.0f, -1.0f), aspect);
+    const float v = __fsub_rn(1.0f, __fadd_rn(y, y));
     float mask = 1.0f;
     float d[3];
     if (c.model == 0) {
-        float w = 1.0f / tanf(c.fov * 0.5f);
+        const float s = __fdiv_rn(1.0f, tanf(__fmul_rn(c.fov, 0.5f)));
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-            d[k] = w * c.forward[k] + u * c.right[k] + v * c.up[k];
+            d[k] = __fmaf_rn(v, c.up[k], __fmaf_rn(s, c.forward[k], __fmul_rn(u, c.right[k])));
     } else {
-        float theta = atan2f(v, u);
-        float phi = c.fov * sqrtf(u * u + v * v);
+        const float theta = atan2f(v, u);
+        float phi = __fmul_rn(__fsqrt_rn(__fmaf_rn(u, u, __fmul_rn(v, v))), c.fov);
         if (phi >= 3.14159265358979323846f) {
             phi = 3.14159265358979323846f - 1e-6f;
             mask = 0.0f;
         }
+        const float sp = sinf(phi);
+        const float a = __fmul_rn(sp, cosf(theta)), b = __fmul_rn(sp, sinf(theta));
+        const float cp = cosf(phi);
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-            d[k] = sinf(phi) * cosf(theta) * c.right[k] + sinf(phi) * sinf(theta) * c.up[k] +
-                   cosf(phi) * c.forward[k];
+            d[k] = __fmaf_rn(cp, c.forward[k], __fmaf_rn(b, c.up[k], __fmul_rn(a, c.right[k])));
     }
     float n2 = __fmaf_rn(d[0], d[0], __fmaf_rn(d[1], d[1], __fmul_rn(d[2], d[2])));
     if (n2 > 0.0f) {
@@ -1461,9 +928,10 @@ __device__ __forceinline__ void cast_ray(const CameraParams &c, int i, int j, Ra
     ray.ox = c.position[0];
     ray.oy = c.position[1];
     ray.oz = c.position[2];
-    ray.dx = d[0] * mask;
-    ray.dy = d[1] * mask;
-    ray.dz = d[2] * mask;
+    ray.dx = __fmul_rn(d[0], mask);
+    ray.dy = __fmul_rn(d[1], mask);
+    ray.dz = __fmul_rn(d[2], mask);
+    ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
 }
 
 // make_rgba8 (tracing_utils.cuh:105-115): clamp, truncate
@@ -1472,7 +940,8 @@ __device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b, float 
     g = fmaxf(0.0f, fminf(1.0f, g));
     b = fmaxf(0.0f, fminf(1.0f, b));
     a = fmaxf(0.0f, fminf(1.0f, a));
-    int ri = (int)(r * 255.0f), gi = (int)(g * 255.0f), bi = (int)(b * 255.0f), ai = (int)(a * 255.0f);
+    int ri = (int)__fmul_rn(r, 255.0f), gi = (int)__fmul_rn(g, 255.0f), bi = (int)__fmul_rn(b, 255.0f),
+        ai = (int)__fmul_rn(a, 255.0f);
     return ((uint32_t)ai << 24) | ((uint32_t)bi << 16) | ((uint32_t)gi << 8) | (uint32_t)ri;
 }
 

@@ -242,16 +242,6 @@ int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t b
 template <typename Faces>
 int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape,
                           uint32_t blocks, cudaStream_t stream) {
-    const char *variant_env = getenv("RFB_FWD_VARIANT"); // experiments: 1 warp-voted face scan, 2 two-pass scan
-    const int fwd_variant = variant_env ? atoi(variant_env) : 0;
-    if (deg == 3 && (fwd_variant == 1 || fwd_variant == 2)) {
-        if (fwd_variant == 1)
-            RFB_LAUNCH((forward_record_voted_kernel<3, Faces, 1>), blocks, kBlock, 0, stream, fp, fa, tape);
-        else
-            RFB_LAUNCH((forward_record_voted_kernel<3, Faces, 2>), blocks, kBlock, 0, stream, fp, fa, tape);
-        RFB_LAUNCHED();
-        return 0;
-    }
     switch (deg) {
     case 0: RFB_LAUNCH((forward_record_kernel<0, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
     case 1: RFB_LAUNCH((forward_record_kernel<1, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
@@ -343,68 +333,25 @@ int launch_backward_cached_cfg(const BackwardParams &bp, const Faces &fa, const 
                                                                                      stream);
 }
 
-template <typename Faces, int SLOTS, int MIN_GROUP, bool REPLAY>
-int launch_backward_pooled_one(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
-                               cudaStream_t stream) {
-    constexpr size_t smem = (size_t)(kBlock / 32) * (32 * 8 + 32 * 16 + SLOTS * grad_row(3) + 128 + SLOTS) * sizeof(float);
-    static_assert(smem <= 48 * 1024, "needs the dynamic shared-memory opt-in");
-    RFB_LAUNCH((backward_pooled_kernel<3, Faces, SLOTS, MIN_GROUP, 5, REPLAY>), blocks, kBlock, smem, stream, bp, fa,
-               tape);
-    RFB_LAUNCHED();
-    return 0;
-}
-
-// EXPERIMENT (RFB_BWD_VARIANT=4..8): pooled-row backward, see foam_kernels.cuh.  Same tape protocol as above.
-template <typename Faces, int SLOTS, int MIN_GROUP>
-int launch_backward_pooled(const BackwardParams &bp, const Faces &fa, const Tape &tape, uint32_t blocks,
-                           cudaStream_t stream) {
-    if (tape.pool)
-        if (int rc = launch_backward_pooled_one<Faces, SLOTS, MIN_GROUP, true>(bp, fa, tape, blocks, stream))
-            return rc;
-    return launch_backward_pooled_one<Faces, SLOTS, MIN_GROUP, false>(bp, fa, tape, blocks, stream);
-}
-
-template <int DEG, typename Faces>
-int launch_backward_cached_deg(int variant, const BackwardParams &bp, const Faces &fa, const Tape &tape,
-                               uint32_t blocks, cudaStream_t stream) {
-    // Shipped configuration: 4 cache slots per warp, groups of >= 6 lanes go through the cache,
-    // 5 CTAs/SM (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200):
-    //   re-walk backward: direct 29.3 ms; (32 slots, >=2 lanes, 4 CTAs) 21.5; (16, >=4, 5) 17.7;
-    //                     (16, >=8, 5) 16.6; (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower;
-    //   replay backward:  (8, >=8, 5) 11.2; (4, >=8) 11.2; (2, >=8) 11.2; (4, >=4) 10.8;
-    //                     (4, >=5) 10.5; (2, >=6) 10.5; (4, >=6) 10.46  <- shipped
-    // (profiles/r01_backward_variants*.json).  With 4 slots the CTA's shared memory drops below
-    // 32 KB, so 5 CTAs fit the 164 KB carve-out and the SM keeps 92 KB of L1 instead of 60.
-    // RFB_BWD_VARIANT selects neighbours for re-tuning on other scenes.
-    switch (variant) {
-    case 1: return launch_backward_cached_cfg<DEG, Faces, 8, 8, 5>(bp, fa, tape, blocks, stream);
-    case 2: return launch_backward_cached_cfg<DEG, Faces, 4, 5, 5>(bp, fa, tape, blocks, stream);
-    case 3: return launch_backward_cached_cfg<DEG, Faces, 2, 6, 5>(bp, fa, tape, blocks, stream);
-    default: return launch_backward_cached_cfg<DEG, Faces, 4, 6, 5>(bp, fa, tape, blocks, stream);
-    }
-}
-
+// Shipped configuration: 4 cache slots per warp, groups of >= 6 lanes go through the cache, 5 CTAs/SM
+// (<= 102 registers).  Measured on the 1M-point / 1080p frame (B200, profiles/r01_backward_variants*.json,
+// profiles/r02_variant_bench.json):
+//   re-walk backward: direct 29.3 ms; (32 slots, >=2 lanes, 4 CTAs) 21.5; (16, >=4, 5) 17.7;
+//                     (16, >=8, 5) 16.6; (8, >=8, 5) 15.7; 6 CTAs/SM spills and is slower;
+//   replay backward:  (8, >=8, 5) 11.2; (4, >=8) 11.2; (2, >=8) 11.2; (4, >=4) 10.8;
+//                     (4, >=5) 10.5; (2, >=6) 10.5; (4, >=6) 10.45  <- shipped
+//   a pooled-row kernel (every group through a 8/16/32-row cache, compact records, quarter-warp rounds):
+//                     12.4 - 14.5 ms -- 0.36x the reductions but +50 % instructions; built, measured, removed.
+// With 4 slots the CTA's shared memory drops below 32 KB, so 5 CTAs fit the 164 KB carve-out and the SM keeps
+// 92 KB of L1 instead of 60.
 template <typename Faces>
 int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, const Tape &tape,
                            uint32_t blocks, cudaStream_t stream) {
-    const char *v = getenv("RFB_BWD_VARIANT");
-    int variant = v ? atoi(v) : 0;
     switch (deg) {
-    case 0: return launch_backward_cached_deg<0>(0, bp, fa, tape, blocks, stream);
-    case 1: return launch_backward_cached_deg<1>(0, bp, fa, tape, blocks, stream);
-    case 2: return launch_backward_cached_deg<2>(0, bp, fa, tape, blocks, stream);
-    default:
-        if (variant == 4)
-            return launch_backward_pooled<Faces, 16, 1>(bp, fa, tape, blocks, stream);
-        if (variant == 5)
-            return launch_backward_pooled<Faces, 32, 1>(bp, fa, tape, blocks, stream);
-        if (variant == 6)
-            return launch_backward_pooled<Faces, 8, 1>(bp, fa, tape, blocks, stream);
-        if (variant == 7) // lone lanes reduce directly
-            return launch_backward_pooled<Faces, 16, 2>(bp, fa, tape, blocks, stream);
-        if (variant == 8)
-            return launch_backward_pooled<Faces, 8, 2>(bp, fa, tape, blocks, stream);
-        return launch_backward_cached_deg<3>(variant, bp, fa, tape, blocks, stream);
+    case 0: return launch_backward_cached_cfg<0, Faces, 4, 6, 5>(bp, fa, tape, blocks, stream);
+    case 1: return launch_backward_cached_cfg<1, Faces, 4, 6, 5>(bp, fa, tape, blocks, stream);
+    case 2: return launch_backward_cached_cfg<2, Faces, 4, 6, 5>(bp, fa, tape, blocks, stream);
+    default: return launch_backward_cached_cfg<3, Faces, 4, 6, 5>(bp, fa, tape, blocks, stream);
     }
 }
 
@@ -558,61 +505,10 @@ int rfb_farthest_neighbor(const float *points, uint32_t num_points, const uint32
         return fail("rfb_farthest_neighbor: NULL argument");
     // point_adjacency may be NULL only when every row is empty; the kernels never read it then
     cudaStream_t stream = (cudaStream_t)stream_;
-    // Variants, all verified bit-identical to the reference's kernel on a B200 (profiles/r01_farthest_neighbor.json);
-    // RFB_FARTHEST_VARIANT picks one for measurement (tests/tools/farthest_bench.py):
-    //   3  8 lanes per row, caller's [N][3] points, fp32 fma accumulation           (default: fastest measured)
-    //   0  the same with the literal fp64 accumulation (F2F/DFMA bound: 0.164 vs 0.128 ms at 1M points)
-    //   1  8 lanes per row, float4 point mirror, fp32 fma accumulation
-    //   2  one thread per row, float4 point mirror, fp32 fma accumulation
-    //   4  one thread per row, caller's points, fp32 fma accumulation (the reference's shape)
-    const char *env = getenv("RFB_FARTHEST_VARIANT");
-    const int variant = env ? atoi(env) : 3;
-    const uint32_t row_grid = (uint32_t)(((uint64_t)num_points + 255) / 256);
-    const uint32_t lane_grid = (uint32_t)(((uint64_t)num_points * rfb::kRowLanes + 255) / 256);
-    const rfb::PackedPoints packed{points};
-    if (variant == 1 || variant == 2) {
-        // stream-ordered scratch; keep freed blocks in the pool (the default threshold of 0 returns them to the
-        // driver at the next synchronisation: 2 ms per call measured)
-        static std::once_flag pool_once;
-        std::call_once(pool_once, [] {
-            int dev = 0;
-            cudaMemPool_t pool = nullptr;
-            uint64_t keep = ~0ull;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            cudaGetLastError();
-        });
-        float4 *mirror = nullptr;
-        if (cudaMallocAsync(&mirror, sizeof(float4) * (size_t)num_points, stream) != cudaSuccess) {
-            cudaGetLastError();
-            return fail("rfb_farthest_neighbor: out of device memory for the point mirror");
-        }
-        RFB_LAUNCH((rfb::pad_points_kernel), row_grid, 256, 0, stream, points, num_points, mirror);
-        const rfb::PaddedPoints padded{mirror};
-        if (variant == 1)
-            RFB_LAUNCH((rfb::farthest_neighbor_kernel<rfb::PaddedPoints, false>), lane_grid, 256, 0, stream,
-                       padded, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
-        else
-            RFB_LAUNCH((rfb::farthest_neighbor_rows_kernel<rfb::PaddedPoints, false>), row_grid, 256, 0,
-                       stream, padded, point_adjacency, point_adjacency_offsets, num_points, indices,
-                       cell_radius);
-        g_launches += 2;
-        const cudaError_t launched = cudaGetLastError();
-        cudaFreeAsync(mirror, stream); // stream-ordered: after the kernels above, also on the error path
-        RFB_CUDA(launched);
-    } else if (variant == 0) {
-        RFB_LAUNCH((rfb::farthest_neighbor_kernel<rfb::PackedPoints, true>), lane_grid, 256, 0, stream,
-                   packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
-        RFB_LAUNCHED();
-    } else if (variant == 4) {
-        RFB_LAUNCH((rfb::farthest_neighbor_rows_kernel<rfb::PackedPoints, false>), row_grid, 256, 0, stream,
-                   packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
-        RFB_LAUNCHED();
-    } else {
-        RFB_LAUNCH((rfb::farthest_neighbor_kernel<rfb::PackedPoints, false>), lane_grid, 256, 0, stream,
-                   packed, point_adjacency, point_adjacency_offsets, num_points, indices, cell_radius);
-        RFB_LAUNCHED();
-    }
+    const uint32_t grid = (uint32_t)(((uint64_t)num_points + 255) / 256);
+    RFB_LAUNCH((rfb::farthest_neighbor_kernel), grid, 256, 0, stream, points, point_adjacency,
+               point_adjacency_offsets, num_points, indices, cell_radius);
+    RFB_LAUNCHED();
     return 0;
 }
 

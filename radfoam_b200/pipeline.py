@@ -61,6 +61,9 @@ class Pipeline:
         # backward of the same step replays it instead of re-scanning faces
         self.record_tape = True
         self._tape_refs = None
+        # set by the autograd ops around their forward: was autograd recording when the op was applied?
+        # (inside Function.forward grad mode is always off; None = not called through such an op)
+        self.autograd_recording = None
         # unordered ray batches ([R, 6], the reference's training batches: train.py:61) are traced
         # in a coherent order -- sorted by (start cell, direction) -- and the per-ray outputs are
         # scattered back; results are unchanged, neighbouring lanes share cells again
@@ -205,6 +208,24 @@ class Pipeline:
         same = all(r() is t and v == t._version for (r, v), t in zip(refs[:2], (rays_c, start_c)))
         return _lib.FLAG_USE_TAPE if same else 0
 
+    def _backward_expected(self, points, attributes) -> bool:
+        """Will a backward over this forward follow?  (Only then is the walk tape worth recording.)
+        nn.Parameters keep requires_grad under torch.no_grad(), so requires_grad alone is not enough."""
+        if not (points.requires_grad or attributes.requires_grad):
+            return False
+        if self.autograd_recording is not None:  # told by radfoam_b200's autograd ops
+            return bool(self.autograd_recording)
+        if torch.is_grad_enabled():  # direct call: the caller may run trace_backward by hand
+            return True
+        # Grad mode is off: either the caller is under torch.no_grad() (an eval render: no backward), or this
+        # is the forward of somebody else's autograd.Function (radfoam_model/render.py), where it is always
+        # off.  A non-leaf input that requires grad only exists while a graph is being recorded.  With leaves
+        # only, the reference's eval path gives points (a Parameter) with attributes built under no_grad
+        # (scene.py:202-217: requires_grad False); both being trainable leaves means a hand-made training step.
+        if any(t.requires_grad and t.grad_fn is not None for t in (points, attributes)):
+            return True
+        return points.requires_grad and attributes.requires_grad
+
     def _settings(self, weight_threshold, max_intersections):
         s = _lib.TraceSettings(0.001, 1024)  # default_trace_settings(), pipeline.h:15-20
         if weight_threshold is not None:
@@ -278,8 +299,7 @@ class Pipeline:
             depth = torch.empty(batch + [num_q], dtype=torch.float32, device=dev)
             depth_indices = torch.empty(batch + [num_q], dtype=torch.uint32, device=dev)
 
-        record = (self.record_tape and self.cache_scene
-                  and (points.requires_grad or attributes.requires_grad))
+        record = self.record_tape and self.cache_scene and self._backward_expected(points, attributes)
         opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c,
                           _lib.FLAG_RECORD_TAPE if record else 0)
         self._tape_refs = ([(weakref.ref(t), t._version) for t in (rays_c, start_c)]
@@ -315,7 +335,8 @@ class Pipeline:
                 and s_ver == start_c._version):
             return rays_c, start_c, rgb_c, grad_c, dq_c, di_c, dg_c, err_c
         take = self._take
-        return (rays_k, start_k, take(rgb_c, perm), take(grad_c, perm), dq_k if dq_c is not None else None,
+        del dq_k  # the backward's own quantiles are permuted, whatever the forward was given
+        return (rays_k, start_k, take(rgb_c, perm), take(grad_c, perm), take(dq_c, perm),
                 take(di_c, perm), take(dg_c, perm), take(err_c, perm))
 
     def _backward_args(self, points, attributes, point_adjacency, point_adjacency_offsets, rays,

@@ -1,10 +1,22 @@
-"""The render autograd op: mirror of radfoam_model/render.py::TraceRays (lines 10-122).
+"""Autograd op over a :class:`radfoam_b200.Pipeline`.
 
-Same forward/backward contract (inputs, outputs, the ErrorBox side channel), so
-``RadFoamScene.forward`` (radfoam_model/scene.py:236-261) can call it unchanged.  The
-one difference is internal: the non-finite gradient scrub the reference does with two
-boolean-mask passes after the kernel (render.py:98-99) is folded into the backward
-kernel's epilogue.
+Call contract = ``radfoam_model/render.py::TraceRays`` (lines 10-122): nine positional
+arguments ``(pipeline, points, attributes, point_adjacency, point_adjacency_offsets, rays,
+start_point, depth_quantiles, return_contribution)`` in, the 5-tuple ``(rgba, depth,
+contribution, num_intersections, errbox)`` out, gradients for ``points`` and ``attributes``
+only, and ``errbox.ray_error`` (set by the caller between forward and backward) -> ``errbox.point_error``
+(scene.py:497-548 uses that side channel for the densification error map).  The reference's own file
+runs unmodified on a ``Pipeline`` too (tests/test_gpu_reference_op.py); this op is the native
+counterpart, written for this library:
+
+  * tensors go through ``save_for_backward`` (the forward's own ``rgba`` output included), so no
+    tensor -> grad_fn -> ctx -> tensor reference cycle is left for Python's cyclic collector --
+    the graph of a step is freed by reference counting the moment the loss goes out of scope;
+  * ``apply`` notes whether autograd was recording when the op was called and tells the pipeline,
+    which records the walk tape only when a backward can follow (inside ``Function.forward`` grad
+    mode is always off, so the pipeline cannot see that by itself);
+  * non-finite gradient entries are zeroed in the backward kernel's epilogue
+    (``scrub_nonfinite=True``), not by two masked passes over the gradients afterwards.
 """
 from __future__ import annotations
 
@@ -12,44 +24,54 @@ import torch
 
 
 class ErrorBox:
+    """Side channel of the op: ``ray_error`` in (per-ray weights), ``point_error`` out."""
+
+    __slots__ = ("ray_error", "point_error")
+
     def __init__(self):
         self.ray_error = None
         self.point_error = None
 
 
 class TraceRays(torch.autograd.Function):
+    @classmethod
+    def apply(cls, pipeline, *args):
+        noted = hasattr(pipeline, "autograd_recording")
+        if noted:
+            before, pipeline.autograd_recording = pipeline.autograd_recording, torch.is_grad_enabled()
+        try:
+            return super().apply(pipeline, *args)
+        finally:
+            if noted:
+                pipeline.autograd_recording = before
+
     @staticmethod
-    def forward(ctx, pipeline, _points, _attributes, _point_adjacency, _point_adjacency_offsets,
-                rays, start_point, depth_quantiles, return_contribution):
-        ctx.rays = rays
-        ctx.start_point = start_point
-        ctx.depth_quantiles = depth_quantiles
+    def forward(ctx, pipeline, points, attributes, point_adjacency, point_adjacency_offsets, rays,
+                start_point, depth_quantiles, return_contribution):
+        out = pipeline.trace_forward(points, attributes, point_adjacency, point_adjacency_offsets, rays,
+                                     start_point, depth_quantiles=depth_quantiles,
+                                     return_contribution=return_contribution)
+        rgba = out["rgba"]
+        saved = [points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, rgba]
+        ctx.with_depth = depth_quantiles is not None
+        if ctx.with_depth:
+            saved += [depth_quantiles, out["depth_indices"]]
+        ctx.save_for_backward(*saved)
         ctx.pipeline = pipeline
-        ctx.points = _points
-        ctx.attributes = _attributes
-        ctx.point_adjacency = _point_adjacency
-        ctx.point_adjacency_offsets = _point_adjacency_offsets
-
-        results = pipeline.trace_forward(
-            _points, _attributes, _point_adjacency, _point_adjacency_offsets, rays, start_point,
-            depth_quantiles=depth_quantiles, return_contribution=return_contribution)
-        ctx.rgba = results["rgba"]
-        ctx.depth_indices = results.get("depth_indices", None)
-        errbox = ErrorBox()
-        ctx.errbox = errbox
-        return (results["rgba"], results.get("depth", None), results.get("contribution", None),
-                results["num_intersections"], errbox)
+        ctx.errbox = box = ErrorBox()
+        return rgba, out.get("depth"), out.get("contribution"), out["num_intersections"], box
 
     @staticmethod
-    def backward(ctx, grad_rgba, grad_depth, grad_contribution, grad_num_intersections, errbox_grad):
-        del grad_contribution, grad_num_intersections, errbox_grad
-        results = ctx.pipeline.trace_backward(
-            ctx.points, ctx.attributes, ctx.point_adjacency, ctx.point_adjacency_offsets, ctx.rays,
-            ctx.start_point, ctx.rgba, grad_rgba, ctx.depth_quantiles, ctx.depth_indices, grad_depth,
-            ctx.errbox.ray_error, scrub_nonfinite=True)
-        points_grad = results["points_grad"]
-        attr_grad = results["attr_grad"]
-        ctx.errbox.point_error = results.get("point_error", None)
-        del (ctx.rays, ctx.start_point, ctx.pipeline, ctx.rgba, ctx.points, ctx.attributes,
-             ctx.point_adjacency, ctx.point_adjacency_offsets, ctx.depth_quantiles)
-        return (None, points_grad, attr_grad, None, None, None, None, None, None)
+    def backward(ctx, grad_rgba, grad_depth, _grad_contribution, _grad_num_intersections, _grad_box):
+        saved = ctx.saved_tensors
+        points, attributes, adjacency, offsets, rays, start_point, rgba = saved[:7]
+        quantiles, depth_indices = (saved[7], saved[8]) if ctx.with_depth else (None, None)
+        if ctx.with_depth and grad_depth is None:  # depth was returned but not used by the loss
+            grad_depth = torch.zeros_like(quantiles)
+        box = ctx.errbox
+        grads = ctx.pipeline.trace_backward(points, attributes, adjacency, offsets, rays, start_point, rgba,
+                                            grad_rgba, quantiles, depth_indices, grad_depth, box.ray_error,
+                                            scrub_nonfinite=True)
+        box.point_error = grads.get("point_error")
+        ctx.pipeline = None
+        return (None, grads["points_grad"], grads["attr_grad"]) + (None,) * 6

@@ -127,26 +127,42 @@ class ShardedTracer:
 
 
 class ShardedTraceRays(torch.autograd.Function):
-    """TraceRays (radfoam_model/render.py:10-122) over a ShardedTracer: forward on the local
-    ray shard, backward yields the all-reduced scene gradients on every rank."""
+    """The render op (radfoam_b200/render.py) over a ShardedTracer: forward on the local ray shard,
+    backward yields the all-reduced scene gradients on every rank.  Returns
+    ``(rgba, depth, contribution, num_intersections)`` of the local shard."""
+
+    @classmethod
+    def apply(cls, tracer, *args):
+        pipe = tracer.pipeline
+        noted = hasattr(pipe, "autograd_recording")
+        if noted:
+            before, pipe.autograd_recording = pipe.autograd_recording, torch.is_grad_enabled()
+        try:
+            return super().apply(tracer, *args)
+        finally:
+            if noted:
+                pipe.autograd_recording = before
 
     @staticmethod
-    def forward(ctx, tracer, _points, _attributes, _point_adjacency, _point_adjacency_offsets,
-                rays, start_point, depth_quantiles, return_contribution):
-        ctx.saved = (tracer, _points, _attributes, _point_adjacency, _point_adjacency_offsets, rays,
-                     start_point, depth_quantiles)
-        results = tracer.trace_forward(
-            _points, _attributes, _point_adjacency, _point_adjacency_offsets, rays, start_point,
-            depth_quantiles=depth_quantiles, return_contribution=return_contribution)
-        ctx.rgba = results["rgba"]
-        ctx.depth_indices = results.get("depth_indices", None)
-        return (results["rgba"], results.get("depth", None), results.get("contribution", None),
-                results["num_intersections"])
+    def forward(ctx, tracer, points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point,
+                depth_quantiles, return_contribution):
+        out = tracer.trace_forward(points, attributes, point_adjacency, point_adjacency_offsets, rays,
+                                   start_point, depth_quantiles=depth_quantiles,
+                                   return_contribution=return_contribution)
+        saved = [points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, out["rgba"]]
+        ctx.with_depth = depth_quantiles is not None
+        if ctx.with_depth:
+            saved += [depth_quantiles, out["depth_indices"]]
+        ctx.save_for_backward(*saved)  # no output tensor on ctx itself: that would be a reference cycle
+        ctx.tracer = tracer
+        return out["rgba"], out.get("depth"), out.get("contribution"), out["num_intersections"]
 
     @staticmethod
-    def backward(ctx, grad_rgba, grad_depth, grad_contribution, grad_num_intersections):
-        tracer, pts, attrs, adj, off, rays, start, dq = ctx.saved
-        res = tracer.trace_backward(pts, attrs, adj, off, rays, start, ctx.rgba, grad_rgba, dq,
-                                    ctx.depth_indices, grad_depth, scrub_nonfinite=True)
-        ctx.saved = None
-        return (None, res["points_grad"], res["attr_grad"], None, None, None, None, None, None)
+    def backward(ctx, grad_rgba, grad_depth, _grad_contribution, _grad_num_intersections):
+        saved = ctx.saved_tensors
+        pts, attrs, adj, off, rays, start, rgba = saved[:7]
+        dq, didx = (saved[7], saved[8]) if ctx.with_depth else (None, None)
+        res = ctx.tracer.trace_backward(pts, attrs, adj, off, rays, start, rgba, grad_rgba, dq, didx, grad_depth,
+                                        scrub_nonfinite=True)
+        ctx.tracer = None
+        return (None, res["points_grad"], res["attr_grad"]) + (None,) * 6

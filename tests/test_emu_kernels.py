@@ -160,62 +160,6 @@ def test_small_csr_passes_bit_exact(small_scene):
     assert np.array_equal(emu.nearest_point(f.points, queries), d2.argmin(axis=1).astype(np.uint32))
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "4"])
-def test_farthest_neighbor_variants_bit_exact(variant, monkeypatch):
-    monkeypatch.setenv("RFB_FARTHEST_VARIANT", variant)
-    g = common.farthest_edge_case()
-    idx, radius = emu.farthest_neighbor(g.points, g.adjacency, g.offsets)
-    ref_idx, ref_radius = oracle.farthest_neighbor(g.points, g.adjacency, g.offsets)
-    assert np.array_equal(idx, ref_idx)
-    common.assert_same_floats(radius, ref_radius)
-
-
-@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5", "6", "7", "8"])
-def test_backward_variants_incl_pooled_rows(variant, long_walk_scene, monkeypatch):
-    """RFB_BWD_VARIANT: 1-3 neighbouring cache configurations, 4-6 the experimental pooled-row kernel (compact records,
-    quarter-warp group sums, position gradients inside the row).  Re-walk and tape replay, image and flat batches."""
-    monkeypatch.setenv("RFB_BWD_VARIANT", variant)
-    for case in (long_walk_scene, common.config1(3, 2)):
-        ref = oracle.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
-        rb = oracle.trace_backward(*scene(case), case.rays, case.start, np.asarray(ref["rgba"]), case.grad_rgba,
-                                   case.quantiles, np.asarray(ref["depth_indices"]), case.grad_depth)
-        pipe = emu.EmuPipeline(3)
-        fwd = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
-        check_backward(pipe.trace_backward(*scene(case), case.rays, case.start, fwd["rgba"], case.grad_rgba,
-                                           case.quantiles, fwd["depth_indices"], case.grad_depth), rb)
-        for _ in range(2):  # second recording: pool large enough, so the replay kernel does the work
-            rec = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, scene_version=9,
-                                     record_tape=True)
-        assert not pipe.tape_status()["overflowed"]
-        check_backward(pipe.trace_backward(*(None,) * 6, rec["rgba"], case.grad_rgba, None, rec["depth_indices"],
-                                           case.grad_depth, scene_version=9, use_tape=True), rb)
-    flat = common.config1(3, 2)
-    rays, start = flat.rays.reshape(-1, 6), flat.start.reshape(-1)
-    dq, gd = flat.quantiles.reshape(-1, 2), flat.grad_depth.reshape(-1, 2)
-    ref = oracle.trace_forward(*scene(flat), rays, start, dq)
-    rb = oracle.trace_backward(*scene(flat), rays, start, np.asarray(ref["rgba"]), flat.grad_rgba.reshape(-1, 4), dq,
-                               np.asarray(ref["depth_indices"]), gd)
-    pipe = emu.EmuPipeline(3)
-    fwd = pipe.trace_forward(*scene(flat), rays, start, dq)
-    check_backward(pipe.trace_backward(*scene(flat), rays, start, fwd["rgba"], flat.grad_rgba.reshape(-1, 4), dq,
-                                       fwd["depth_indices"], gd), rb)
-
-
-def test_pooled_rows_issue_fewer_reductions(long_walk_scene, monkeypatch):
-    """The point of the pooled-row kernel, counted on the emulator: fewer 16-byte reductions than the shipped one."""
-    case = long_walk_scene
-    counts = {}
-    for variant in ("0", "4"):
-        monkeypatch.setenv("RFB_BWD_VARIANT", variant)
-        pipe = emu.EmuPipeline(3)
-        fwd = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles)
-        emu.red_counters()
-        pipe.trace_backward(*scene(case), case.rays, case.start, fwd["rgba"], case.grad_rgba, case.quantiles,
-                            fwd["depth_indices"], case.grad_depth)
-        counts[variant] = emu.red_counters()["bytes"]
-    assert counts["4"] < 0.85 * counts["0"]   # 0.73 on this 512-ray scene; 0.36 at 100k rays (profiles/r01_emulated_reduction_counts.json)
-
-
 @pytest.mark.parametrize("tag", ["f16", "f32"])
 @pytest.mark.parametrize("model", ["pinhole", "fisheye"])
 def test_trace_benchmark_against_reference_kernel_frames(tag, model):
@@ -274,8 +218,7 @@ def test_emulated_kernels_against_reference_kernel_golden_vectors(path):
 
 
 @pytest.mark.parametrize("seed", ["1", "2", "3"])
-@pytest.mark.parametrize("variant", ["0", "4", "7"])
-def test_backward_under_shuffled_lane_schedules(seed, variant, long_walk_scene, monkeypatch, tmp_path):
+def test_backward_under_shuffled_lane_schedules(seed, long_walk_scene, monkeypatch, tmp_path):
     """A poor man's racecheck for warp-level synchronisation: the emulator resumes the lanes of a CTA in a different
     pseudo-random order on every scheduling pass (RFB_EMU_SHUFFLE), so a shared-memory read that is not separated from
     another lane's write by a __syncwarp gives wrong gradients.  Runs in a subprocess: the order is fixed at load."""
@@ -304,42 +247,9 @@ for use_tape in (True, False):
         assert common.grad_error(bwd[k], np.asarray(rb[k])) <= 2e-5, (k, use_tape)
 print("ok")
 """
-    env = dict(os.environ, RFB_EMU_SHUFFLE=seed, RFB_BWD_VARIANT=variant)
+    env = dict(os.environ, RFB_EMU_SHUFFLE=seed)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
-
-
-@pytest.mark.parametrize("fwd_variant", ["1", "2"])
-def test_experimental_face_scans_are_bit_identical(fwd_variant, long_walk_scene, small_scene, monkeypatch):
-    """RFB_FWD_VARIANT=1 / 2 (experiments): the recording forward with the warp-voted or the two-pass face scan must
-    reproduce the shipped recording forward bit for bit -- outputs and tape -- on image and edge cases."""
-    cases = [long_walk_scene, small_scene, common.config1(3, 2)]
-    rays = common.config1(3, 2).rays.copy()
-    rays[0, 0, 3:] = 0.0
-    rays[0, 1, 3:] = [np.nan, 0, 1]
-    weird = common.config1(3, 2)
-    for case in cases:
-        outs = {}
-        for variant in ("0", fwd_variant):
-            monkeypatch.setenv("RFB_FWD_VARIANT", variant)
-            pipe = emu.EmuPipeline(3)
-            for _ in range(2):
-                rec = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, scene_version=4,
-                                         record_tape=True)
-            h, w = case.rays.shape[:2]
-            outs[variant] = (rec, emu.tape_records(pipe, h, w))
-        for k in outs["0"][0]:
-            assert np.array_equal(outs["0"][0][k].view(np.uint32), outs[fwd_variant][0][k].view(np.uint32)), k
-        for a, b in zip(outs["0"][1], outs[fwd_variant][1]):
-            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
-                                  b.view(np.uint32) if b.dtype == np.float32 else b)
-    monkeypatch.setenv("RFB_FWD_VARIANT", fwd_variant)
-    pipe = emu.EmuPipeline(3)
-    got = pipe.trace_forward(*scene(weird), rays, weird.start, weird.quantiles, scene_version=4, record_tape=True,
-                             max_intersections=7)
-    ref = oracle.trace_forward(*scene(weird), rays, weird.start, weird.quantiles, max_intersections=7)
-    check_forward_nan_aware = np.array_equal(got["num_intersections"].reshape(-1), np.asarray(ref["num_intersections"]).reshape(-1))
-    assert check_forward_nan_aware
 
 
 @pytest.mark.parametrize("world", [2, 3])

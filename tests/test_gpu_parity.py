@@ -287,8 +287,7 @@ def test_trace_benchmark(torch_cuda, model, attr_dtype):
     torch.cuda.synchronize()
     a = out.cpu().numpy().view(np.uint8).reshape(120, 200, 4).astype(np.int32)
     b = ref_out.cpu().numpy().view(np.uint8).reshape(120, 200, 4).astype(np.int32)
-    assert np.abs(a - b).max() <= 1
-    assert (a != b).any(axis=-1).mean() < 2e-3
+    assert np.array_equal(a, b), f"{int((a != b).any(axis=-1).sum())} pixels differ from the reference's bytes"
     assert (b[..., :3].sum(axis=-1) > 0).mean() > 0.2  # the frame is not empty
 
 
@@ -553,35 +552,4 @@ def test_pt_checkpoint_benchmark_loop(torch_cuda, tmp_path):
                                     weight_threshold=0.05)
             torch.cuda.synchronize()
             b = ref_out.cpu().numpy().view(np.uint8).reshape(height, width, 4).astype(np.int32)
-            assert np.abs(a - b).max() <= 1 and (a != b).any(axis=-1).mean() < 2e-3
-
-
-# ------------------------------------------------------------------ experimental kernels (opt-in)
-@pytest.mark.skipif(not __import__("os").environ.get("RFB_TEST_EXPERIMENTS"),
-                    reason="experimental backward variants: set RFB_TEST_EXPERIMENTS=1 (emulator-checked on the CPU, "
-                           "tests/test_emu_kernels.py; not part of the shipped path)")
-@pytest.mark.parametrize("variant", ["4", "5", "6", "7", "8"])
-def test_experimental_pooled_backward_matches_reference_kernels(torch_cuda, variant, monkeypatch):
-    monkeypatch.setenv("RFB_BWD_VARIANT", variant)
-    for case in (common.config1(3, 2), common.scene_case(num_points=60000, width=320, height=200)):
-        ref = run_ref_gpu(torch_cuda, case)
-        for tape in (False, True):
-            got = run_ours(torch_cuda, case, tape=tape, repeat=2 if tape else 1)
-            for k in ("points_grad", "attr_grad"):
-                assert common.grad_error(got[k], ref[k]) <= GRAD_TOL, (variant, tape, k)
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("RFB_TEST_EXPERIMENTS"),
-                    reason="experimental forward variant: set RFB_TEST_EXPERIMENTS=1")
-@pytest.mark.parametrize("fwd_variant", ["1", "2"])
-def test_experimental_forward_scans_are_bit_identical(torch_cuda, fwd_variant, monkeypatch):
-    for case in (common.config1(3, 2), common.scene_case(num_points=60000, width=320, height=200),
-                 common.scene_case(num_points=60000, width=320, height=200, inside=True)):
-        monkeypatch.setenv("RFB_FWD_VARIANT", "0")
-        base = run_ours(torch_cuda, case, tape=True, repeat=2)
-        monkeypatch.setenv("RFB_FWD_VARIANT", fwd_variant)
-        got = run_ours(torch_cuda, case, tape=True, repeat=2)
-        for k in ("rgba", "depth", "depth_indices", "num_intersections"):
-            assert np.array_equal(got[k].view(np.uint32), base[k].view(np.uint32)), k
-        for k in ("points_grad", "attr_grad"):          # replayed from the voted forward's tape
-            assert common.grad_error(got[k], base[k]) <= GRAD_TOL, k
+            assert np.array_equal(a, b), f"{int((a != b).any(axis=-1).sum())} pixels differ from the reference's bytes"

@@ -1,4 +1,5 @@
-"""Time backward variants (RFB_BWD_MODE / RFB_BWD_VARIANT env switches) on one foam."""
+"""Kernel times on the bench frame: forward (plain / recording), backward (direct, re-walk with the warp cache,
+tape replay), with the replay's gradient error against the direct kernel."""
 import json
 import os
 import sys
@@ -34,7 +35,6 @@ os.environ["RFB_BWD_MODE"] = "direct"
 base = bwd()
 res["direct_ms"] = timeit(bwd)
 os.environ["RFB_BWD_MODE"] = "cached"
-os.environ["RFB_BWD_VARIANT"] = "0"
 out = bwd()
 res["rewalk_v0_ms"] = timeit(bwd)
 print("rewalk", res["rewalk_v0_ms"], flush=True)
@@ -43,29 +43,11 @@ scene[0].requires_grad_(True)
 pipe.record_tape = True
 fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res["fwd_record_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
-# experimental recording forwards (RFB_FWD_VARIANT=1 warp-voted face scan, 2 two-pass scan): time + bit-identity
-os.environ["RFB_FWD_VARIANT"] = "0"
-fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
-for fv, name in ((1, "voted"), (2, "two_pass")):
-    os.environ["RFB_FWD_VARIANT"] = str(fv)
-    alt = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
-    res[f"fwd_record_{name}_ms"] = timeit(lambda: pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"]))
-    res[f"fwd_record_{name}_identical"] = bool(all(
-        torch.equal(alt[k].view(torch.int32) if alt[k].dtype != torch.float16 else alt[k],
-                    fwd[k].view(torch.int32) if fwd[k].dtype != torch.float16 else fwd[k])
-        for k in ("rgba", "depth", "depth_indices", "num_intersections")))
-os.environ["RFB_FWD_VARIANT"] = "0"
-fwd = pipe.trace_forward(*scene, fr["rays"], fr["start"], depth_quantiles=fr["dq"])
 res["tape"] = pipe.tape_status()
-# 0 shipped; 1-3 neighbouring cache configurations; 4/5/6 the experimental pooled-row kernel (16/32/8 rows);
-# 7/8 the same with lone lanes reducing directly (16/8 rows)
-for v in (int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5,6,7,8").split(",")):
-    os.environ["RFB_BWD_VARIANT"] = str(v)
-    out = bwd()
-    res[f"replay_v{v}_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
-    res[f"replay_v{v}_points_err_vs_direct"] = float((out["points_grad"] - base["points_grad"]).abs().max() / base["points_grad"].abs().max())
-    res[f"replay_v{v}_ms"] = timeit(bwd)
-    print(v, res[f"replay_v{v}_ms"], flush=True)
+out = bwd()
+res["replay_err_vs_direct"] = float((out["attr_grad"] - base["attr_grad"]).abs().max() / base["attr_grad"].abs().max())
+res["replay_points_err_vs_direct"] = float((out["points_grad"] - base["points_grad"]).abs().max() / base["points_grad"].abs().max())
+res["replay_ms"] = timeit(bwd)
 print(json.dumps(res, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/variant_bench.json", "w"), indent=1)
