@@ -61,6 +61,12 @@ def load_or_build_foam(num_points: int, log):
     return f
 
 
+def workload_name(f, width: int, height: int) -> str:
+    """Identical in both arms (the driver compares the strings)."""
+    return (f"config4: synthetic foam {f.num_points} points (E={f.adjacency.size}), {width}x{height} frame, "
+            "Q=2, sh_degree 3, fwd+bwd")
+
+
 def make_frame(f, width: int, height: int):
     from radfoam_b200 import foam
 
@@ -197,6 +203,18 @@ def algorithmic_bytes(num_steps: int, num_rays: int, mean_degree: float, attr_di
     return (num_steps * b_f + num_rays * fixed_f, num_steps * b_b + num_rays * fixed_b, b_f, b_b)
 
 
+def compulsory_bytes(num_steps: int, num_rays: int, cells: int, mean_degree: float, attr_dim: int, q: int):
+    """DRAM bytes one launch cannot avoid (SURVEY.md §8d's compulsory bound): unique cells x row bytes + the
+    tape + per-ray inputs/outputs.  forward (records): per touched cell 16 (cell) + 8 (offsets) + 12*deg
+    (face + neighbour rows) + 4*(A-1) (SH row); 8 per ray-step (tape write); per ray 24 + 4 + 16 + 4 + 20 q + 8.
+    backward (replays): per touched cell 16 + 4*(A-1) + 2 * 4 * grad_row (accumulator read-modify-write);
+    8 per ray-step (tape read); per ray 24 + 4 + 16 + 16 + 20 q + 8."""
+    grad_row = ((attr_dim - 1 + 3) // 4) * 4 + 4
+    fwd = cells * (16 + 8 + 12 * mean_degree + 4 * (attr_dim - 1)) + 8 * num_steps + num_rays * (56 + 20 * q)
+    bwd = cells * (16 + 4 * (attr_dim - 1) + 8 * grad_row) + 8 * num_steps + num_rays * (68 + 20 * q)
+    return {"forward_kernel": float(fwd), "backward_kernel": float(bwd)}
+
+
 def dist_setup(gpus: int):
     import torch
     import torch.distributed as dist
@@ -290,12 +308,20 @@ def run_ours(args):
     adj, off = d(f.adjacency), d(f.offsets)
     pipe = radfoam_b200.create_pipeline(3, "float32")
     tracer = sharded.ShardedTracer(pipe)
+    if args.emulate_shard and world == 1:
+        # profiling aid: trace rank 0's shard of an N-way split on ONE GPU (no collective) -- the per-GPU
+        # work of the N-GPU run, e.g. for an ncu capture at the N = 8 shard size
+        tracer.rank, tracer.world = 0, int(args.emulate_shard)
 
     # this rank's shard of every per-ray tensor (interleaved 8-row bands)
     host = {k: torch.from_numpy(v) for k, v in frame.items()}
     shard_host = {k: tracer.shard(v, image=True).contiguous().pin_memory() for k, v in host.items()}
+    if args.emulate_shard and world == 1:
+        tracer.rank, tracer.world = 0, 1  # shards are cut; from here on behave as a single rank
     dv = {k: v.to(dev) for k, v in shard_host.items()}
     R_local = dv["rays"].shape[0] * dv["rays"].shape[1]
+    if args.emulate_shard and world == 1:
+        R_total = R_local  # the line then describes the shard alone
 
     def step_device():
         pipe.invalidate_cache()  # new parameter values every training step
@@ -374,6 +400,12 @@ def run_ours(args):
     nint_local = fwd["num_intersections"].to(torch.int64)
     steps_local = int(nint_local.sum().item())
     n_mean, n_max = float(nint_local.float().mean().item()), int(nint_local.max().item())
+    # cells this rank's rays composite at least once (for the compulsory-traffic bound of the roofline)
+    with torch.no_grad():
+        contrib = pipe.trace_forward(points, attrs, adj, off, dv["rays"], dv["start"],
+                                     return_contribution=True)["contribution"]
+    cells_touched = int((contrib > 0).sum().item())
+    del contrib
 
     # --- timed region: exactly K steps, events on the launching stream, max over ranks
     pipe.set_profiling(True)
@@ -393,13 +425,29 @@ def run_ours(args):
     total_ms = max_over_ranks(ev0.elapsed_time(ev1), world)
     clocks = sampler.stop() if sampler else None
     launches = rp.launch_count()
-    if not args.kernel_times:
-        # kernel durations from a separate short pass so that the event waits above do not
-        # serialise the timed loop
-        for _ in range(3):
-            step_device()
-            fwd_ms.append(pipe.last_kernel_ms("forward"))
-            bwd_ms.append(pipe.last_kernel_ms("backward"))
+    # per-phase durations from a separate short pass (events between the phases would serialise the timed loop)
+    phase_rows = []
+    for _ in range(3):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        pipe.invalidate_cache()
+        ev[0].record()
+        fwd = tracer.trace_forward(points, attrs, adj, off, dv["rays"], dv["start"], depth_quantiles=dv["dq"])
+        ev[1].record()
+        acc, _ = pipe.trace_backward_accumulate(points, attrs, adj, off, dv["rays"], dv["start"], fwd["rgba"],
+                                                dv["grad_rgba"], dv["dq"], fwd["depth_indices"], dv["grad_depth"])
+        ev[2].record()
+        tracer.reduce_and_finalize(points.shape[0], dev, True, acc)
+        ev[3].record()
+        torch.cuda.synchronize()
+        kf, kb = pipe.last_kernel_ms("forward"), pipe.last_kernel_ms("backward")
+        if not args.kernel_times:
+            fwd_ms.append(kf)
+            bwd_ms.append(kb)
+        phase_rows.append([ev[0].elapsed_time(ev[1]) - kf, kf, ev[1].elapsed_time(ev[2]) - kb, kb,
+                           ev[2].elapsed_time(ev[3])])
+    phase_names_dev = ("relayout_and_tape_setup", "forward_kernel", "accumulator_zero_fill", "backward_kernel",
+                       "grad_reduce_and_finalize")
+    phases_ms = {n: round(float(np.median([r[j] for r in phase_rows])), 4) for j, n in enumerate(phase_names_dev)}
     pipe.set_profiling(False)
     ms_per_step = total_ms / args.steps
 
@@ -452,22 +500,25 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # --- roofline of the dominant kernel (backward ray kernel), this rank's launch
+    # --- roofline of the dominant kernel (the backward ray kernel), this rank's launch
     peak, peak_src = measured_peak_hbm()
     mean_deg = f.adjacency.size / f.num_points
     bytes_f, bytes_b, b_f, b_b = algorithmic_bytes(steps_local, R_local, mean_deg, 49, 2)
     k_fwd, k_bwd = float(np.mean(fwd_ms)), float(np.mean(bwd_ms))
     dominant = "backward_kernel" if k_bwd >= k_fwd else "forward_kernel"
-    dom_bytes, dom_ms = (bytes_b, k_bwd) if k_bwd >= k_fwd else (bytes_f, k_fwd)
+    gather_bytes, dom_ms = (bytes_b, k_bwd) if k_bwd >= k_fwd else (bytes_f, k_fwd)
+    comp = compulsory_bytes(steps_local, R_local, cells_touched, mean_deg, 49, 2)
+    dom_bytes = comp[dominant]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    limits = {}
+    lpath = os.path.join(ROOT, "profiles", "kernel_limits.json")
+    if os.path.exists(lpath):
         try:
-            traffic = json.load(open(tpath)).get(dominant)
+            limits = json.load(open(lpath))
         except (OSError, ValueError):
-            traffic = None
-
+            limits = {}
+    lim = limits.get(dominant, {})
+    traffic = lim.get("dram_bytes_per_launch") if world == 1 and not args.emulate_shard else None
     cpu = cpu_baseline(f, frame, log) if not args.no_cpu_baseline else None
     try:
         tape = pipe.tape_status()
@@ -479,10 +530,13 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": f"config4: synthetic foam {f.num_points} points (E={f.adjacency.size}), "
-                               f"{W}x{H} frame, Q=2, sh_degree 3, fwd+bwd, scene re-layout every step",
+        "config": {"workload": workload_name(f, W, H),
+                   "step": "scene re-layout (parameters change every training step) + trace_forward + "
+                           "trace_backward" + (f"; rank 0's shard of a {args.emulate_shard}-way ray split only"
+                                               if args.emulate_shard else ""),
                    "rays": R_total, "mean_cells_per_ray": n_mean, "max_cells_per_ray": n_max,
-                   "parallelism": f"ray-sharded x{world} (8-row bands), 1 all-reduce of [N,52] fp32"
+                   "parallelism": f"ray-sharded x{world} (8-row bands), {tracer.reduction_name()} of the [N,52] fp32 "
+                                  "gradient accumulator"
                    if world > 1 else "single GPU",
                    "l2": "scene working set (417 MB) larger than L2 (126 MB); no explicit flush"},
         "clocks": clocks,
@@ -493,16 +547,29 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "kernels_ms": {"forward_kernel": k_fwd, "backward_kernel": k_bwd},
         "walk_tape": tape,
+        "phases_ms": phases_ms,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": dom_bytes,
-                     "bytes_per_ray_step": {"forward": b_f, "backward": b_b},
-                     "ray_steps_per_launch": steps_local,
-                     "note": "achieved = no-reuse algorithmic bytes / kernel time (an EFFECTIVE rate: "
-                             "neighbouring rays re-touch the same cells in L1/L2, so it may exceed the HBM "
-                             "peak); traffic = DRAM bytes ncu measured for the same launch "
-                             "(profiles/traffic.json). The kernels are issue / L2-atomic bound, not DRAM "
-                             "bound: see the ncu summaries under profiles/."},
+                     "algorithmic_model": "compulsory DRAM bytes: every ray-step reads (forward: writes) its 8-byte "
+                                          "tape record once; every cell the launch composites is fetched once "
+                                          "(16 B cell + 192 B SH row; forward also its face row) and its 208 B "
+                                          "gradient row is read and written once; per-ray inputs/outputs once",
+                     "ray_steps_per_launch": steps_local, "cells_touched": cells_touched,
+                     "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                     "traffic_over_algorithmic": (traffic / dom_bytes) if traffic else None,
+                     # what actually limits the kernel (ncu --set full of the same command, profiles/):
+                     "binding_limit": lim.get("binding_limit"),
+                     "binding_frac": lim.get("binding_frac"),
+                     "speed_of_light": lim.get("speed_of_light"),
+                     "source": limits.get("source"),
+                     "effective_gather_gbs": gather_bytes / (dom_ms * 1e-3) / 1e9,
+                     "note": "NOT an HBM-bound kernel: achieved/frac state how little of the HBM roofline the "
+                             "path needs (the cell working set is re-used from L1/L2; most DRAM bytes are the "
+                             "walk tape). The limit that binds is binding_limit (fraction of its peak = "
+                             "binding_frac). effective_gather_gbs is round 1's no-reuse gather model "
+                             "(bytes every ray-step would fetch without any cache), kept for continuity; it "
+                             "is not a bound."},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -656,10 +723,10 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"config4: synthetic foam {f.num_points} points (E={f.adjacency.size}), "
-                               f"{W}x{H} frame, Q=2, sh_degree 3, fwd+bwd; the reference's own CUDA kernels "
-                               "(prefetch_adjacent_diff + forward/backward<float,3,128>, zero-fills, finite "
-                               "scrub) on one B200 -- radfoam ships no CPU or multi-GPU tracing path",
+        "config": {"workload": workload_name(f, W, H),
+                   "step": "the reference's own CUDA kernels (prefetch_adjacent_diff + "
+                           "forward/backward<float,3,128>, zero-fills, finite scrub) on one B200 -- radfoam ships "
+                           "no CPU or multi-GPU tracing path",
                    "rays": R, "mean_cells_per_ray": float(nint.float().mean().item()),
                    "max_cells_per_ray": int(nint.max().item()), "parallelism": "single GPU"},
         "clocks": clocks,
@@ -682,6 +749,8 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", type=int, default=0,
+                    help="single GPU only: trace rank 0's shard of an N-way ray split (profiling aid)")
     ap.add_argument("--kernel-times", action="store_true",
                     help="read per-kernel event timings inside the timed loop (serialises it)")
     args = ap.parse_args()

@@ -85,6 +85,17 @@ typedef struct rfb_launch_opts {
      * reference's adjacent_diff among them, which it rebuilds on every call,
      * pipeline.cu:613-620, 667-674) are reused instead of rebuilt.  0 = rebuild. */
     uint64_t scene_version;
+    /*   PRECONDITIONS of a nonzero scene_version (the library cannot verify them cheaply):
+     *     - the caller MUST pass a new value whenever it has written to points, attributes,
+     *       point_adjacency or point_adjacency_offsets since the last call with the old value
+     *       (in-place optimizer updates included) -- otherwise stale mirrors are traced, silently;
+     *     - the four device pointers MUST stay allocated and unmoved for as long as a value is
+     *       reused (the cache key is pointer + size + version, not contents);
+     *     - a pipeline MUST NOT be used from two streams at once; consecutive calls on different
+     *       streams are ordered by the library (events on the mirrors and on the tape).
+     *   Setting the environment variable RFB_DEBUG=1 makes every cache hit re-checksum points and
+     *   attributes on the device (synchronising) and fail with a message when they changed under
+     *   an unchanged version.  scene_version == 0 is always safe: nothing is cached. */
     /* Nonzero: rays form a row-major image of this width (R % width == 0); rays
      * are then assigned to warps as 8x4 pixel tiles for cell coherence.
      * 0 = rays are an unordered batch (linear assignment).  Results are
@@ -103,7 +114,9 @@ typedef struct rfb_launch_opts {
 /* trace_backward: the caller vouches that rays / start points / quantiles / settings / scene are
  * those of this pipeline's last recording forward; the library additionally checks pointers,
  * sizes, settings and scene_version and silently re-walks when anything differs.  Results are
- * identical either way. */
+ * identical either way.  PRECONDITION: the CONTENTS of rays and start_point_index MUST be
+ * unchanged since that forward (the library compares the pointers, not the data).  If the tape's
+ * memory cannot be allocated the forward simply does not record and the backward re-walks. */
 #define RFB_FLAG_USE_TAPE 4u
 
 typedef struct rfb_pipeline rfb_pipeline;
@@ -190,6 +203,27 @@ uint32_t rfb_grad_row_floats(const rfb_pipeline *pipeline);
 int rfb_trace_backward_finalize(rfb_pipeline *pipeline, uint32_t num_points,
                                 float *points_grad, void *attribute_grad,
                                 uint32_t flags, void *stream);
+
+/* ---- fused cross-GPU reduction + finalize over peer-mapped memory (NVLink / NVSwitch) ----
+ * rfb_set_grad_accumulator: make rfb_trace_backward_accumulate scatter into caller-provided device memory
+ * (16-byte aligned, >= num_points * rfb_grad_row_floats() floats; e.g. a symmetric / IPC-mapped allocation
+ * that the other GPUs of the box can address) instead of the pipeline's own buffer.  NULL restores the
+ * internal buffer.  The memory stays the caller's; accumulate zero-fills it first, as it does its own.
+ *
+ * rfb_reduce_finalize_peers: rank `rank` of `world` (<= 16) sums its share of the rows (blocks of 16 rows
+ * dealt round-robin) over ALL ranks' accumulators peer_acc[0..world) -- device pointers addressable from the
+ * current device, peer_acc[rank] being this rank's own -- in rank order, applies the finalize epilogue
+ * (reference layout, RFB_FLAG_SCRUB_NONFINITE) and stores the finished rows into every rank's
+ * peer_attribute_grad[w] ([N][A], attr dtype) and peer_points_grad[w] ([N][3] f32).  After ALL ranks have run
+ * it every rank holds the complete gradients, bit-identical across ranks.  The CALLER provides the two
+ * cross-GPU barriers: every rank's accumulate must have finished before any rank starts, and every rank must
+ * have finished before the outputs are read or an accumulator is written again. */
+int rfb_set_grad_accumulator(rfb_pipeline *pipeline, float *ptr, uint64_t num_floats);
+int rfb_reduce_finalize_peers(rfb_pipeline *pipeline, uint32_t world, uint32_t rank,
+                              uint32_t num_points, const float *const *peer_acc,
+                              void *const *peer_attribute_grad,
+                              float *const *peer_points_grad, uint32_t flags,
+                              void *stream);
 
 /* forward-only render with in-kernel ray generation (camera.h:56-85) and RGBA8
  * packing (tracing_utils.cuh:105-115).  adjacent_diff is the caller-built

@@ -60,6 +60,9 @@ SIGNATURES = {
     "rfb_grad_accumulator": (c_int, [_P, POINTER(_P), POINTER(c_uint64)]),
     "rfb_grad_row_floats": (c_uint32, [_P]),
     "rfb_trace_backward_finalize": (c_int, [_P, c_uint32, _P, _P, c_uint32, _P]),
+    "rfb_set_grad_accumulator": (c_int, [_P, _P, c_uint64]),
+    "rfb_reduce_finalize_peers": (c_int, [_P, c_uint32, c_uint32, c_uint32, POINTER(_P), POINTER(_P), POINTER(_P),
+                                          c_uint32, _P]),
     "rfb_trace_benchmark": (c_int, [_P, POINTER(TraceSettings), c_uint32, _P, _P, _P, _P, _P,
                                     POINTER(Camera), _P, _P, POINTER(LaunchOpts), _P]),
     "rfb_launch_count": (c_uint64, []),

@@ -16,7 +16,19 @@
 namespace rfb {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kBlock = 128; // threads per CTA in the ray kernels
+// Threads per CTA in the ray kernels.  A CTA's registers / shared memory are only released when its LAST
+// warp finishes, and ray lengths vary widely (mean 97 cells, max 257 on the bench frame), so smaller CTAs
+// keep the SM fuller in the kernel's tail; RFB_KBLOCK (32 / 64 / 128) is a build-time knob so that the
+// choice is measured (tests/tools/kblock_bench.py).
+#ifndef RFB_KBLOCK
+#define RFB_KBLOCK 128
+#endif
+constexpr int kBlock = RFB_KBLOCK;
+static_assert(kBlock == 32 || kBlock == 64 || kBlock == 128, "RFB_KBLOCK must be 32, 64 or 128");
+// a CTA covers kTileW x kTileH pixels: warps of 8x4 pixels, two side by side when there are at least two
+constexpr int kWarpsX = kBlock >= 64 ? 2 : 1;
+constexpr int kWarpsY = kBlock / 32 / kWarpsX;
+constexpr int kTileW = 8 * kWarpsX, kTileH = 4 * kWarpsY;
 
 __host__ __device__ constexpr int sh_dim(int deg) { return (deg + 1) * (deg + 1); }
 // floats per row of the internal SH mirror (3*sh_dim padded to a multiple of 4)
@@ -499,8 +511,8 @@ struct BackwardRay {
 };
 
 // ray index of this thread.  image_width == 0: linear.  Otherwise the rays are a
-// row-major image; a CTA of 128 threads covers a 16x8 pixel block and each warp
-// an 8x4 tile, so the lanes of a warp sit in the same or adjacent cells.
+// row-major image; a CTA covers a kTileW x kTileH pixel block (16x8 at 128 threads) and each
+// warp an 8x4 tile, so the lanes of a warp sit in the same or adjacent cells.
 __device__ __forceinline__ bool thread_ray(uint32_t num_rays, uint32_t image_width,
                                            uint32_t blocks_x, uint32_t &ray_idx) {
     if (image_width == 0) {
@@ -509,8 +521,8 @@ __device__ __forceinline__ bool thread_ray(uint32_t num_rays, uint32_t image_wid
     }
     uint32_t bx = blockIdx.x % blocks_x, by = blockIdx.x / blocks_x;
     uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t x = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    uint32_t y = by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    uint32_t x = bx * kTileW + (warp % kWarpsX) * 8 + (lane & 7);
+    uint32_t y = by * kTileH + (warp / kWarpsX) * 4 + (lane >> 3);
     uint32_t height = num_rays / image_width;
     ray_idx = y * image_width + x;
     return x < image_width && y < height;

@@ -115,6 +115,18 @@ __global__ void adjacent_diff_kernel(const float *__restrict__ points, uint32_t 
     }
 }
 
+// RFB_DEBUG: order-independent checksum of a word array (sum of word * odd multiplier of its index)
+__global__ void checksum_kernel(const uint32_t *__restrict__ words, uint64_t count, unsigned long long *sum) {
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        local += (unsigned long long)words[i] * (2ull * i + 1ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0)
+        atomicAdd(sum, local);
+}
+
 // ------------------------------------------------------------------ forward
 struct ForwardParams {
     const float4 *cells;
@@ -241,7 +253,7 @@ struct Tape {
 // Forward with an explicit warp-synchronous loop (all lanes stay in the loop until the warp is
 // done, so lane 0 can allocate tape chunks for the warp) that records the tape.
 template <int DEG, typename Faces>
-__global__ void __launch_bounds__(kBlock, 7) forward_record_kernel(const ForwardParams p, const Faces fa,
+__global__ void __launch_bounds__(kBlock, 7 * 128 / kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
                                                                 const Tape tape) {
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -520,7 +532,7 @@ __global__ void __launch_bounds__(kBlock) backward_kernel(const BackwardParams p
 // once), so a pool overflow needs no host round trip.  (Prefetching the next cell's SH row into
 // L1 or L2 as soon as the cell is known was tried and is no faster: 11.8 vs 11.65 ms.)
 template <int DEG, typename Faces, int SLOTS, int MIN_GROUP, int MIN_BLOCKS, bool REPLAY>
-__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS * 128 / kBlock)
     backward_cached_kernel(const BackwardParams p, const Faces fa, const Tape tape) {
     if (tape.pool != nullptr) {
         const bool overflowed = tape.ctrl[1] != 0u;
@@ -773,6 +785,126 @@ __global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t nu
                 gq = 0.0f;
             points_grad[3 * (uint64_t)i + lane] = gq;
         }
+    }
+}
+
+// ------------------------------------------------------------------ multi-GPU: fused reduce + finalize
+// The one exchange step of the ray-sharded path: every rank holds a partial gradient
+// accumulator [N][grad_row]; every rank needs the summed gradients in the reference layout.  Instead of
+// ncclAllReduce -> finalize_grads_kernel (two passes over 218 MB per rank at 1 M points plus the collective's
+// own staging), ONE kernel per rank works directly on peer-mapped memory over NVLink / NVSwitch:
+//   * rank r owns the row blocks b = r, r + W, r + 2W, ... (kPeerRows rows each);
+//   * for a block it loads the rows of ALL W accumulators (one local, W - 1 peer loads of 16 bytes per
+//     thread, all in flight together), sums them in rank order (so every rank would compute the same bits),
+//   * applies the finalize epilogue (reference layout [N][A] + [N][3], optional non-finite scrub, fp16
+//     rounding once), staged through shared memory so that the unaligned 49-float rows leave as aligned
+//     16-byte (fp16: 8-byte) stores,
+//   * and stores the finished block into EVERY rank's output arrays (W - 1 peer stores per thread).
+// Per rank: (W-1)/W of the accumulator comes in over NVLink and (W-1)/W of the outputs goes out, both directions
+// at once; no intermediate buffer, no second pass.  The caller brackets the launch with cross-GPU barriers
+// (all accumulators complete / all stores landed): radfoam_b200/sharded.py uses the symmetric-memory signal pads.
+constexpr int kMaxPeers = 16;
+constexpr int kPeerRows = 16; // rows per block: 16 * A floats is a whole number of 16-byte vectors for every A
+
+struct PeerReduceParams {
+    const float *acc[kMaxPeers];
+    void *attr_grad[kMaxPeers];
+    float *points_grad[kMaxPeers];
+    uint32_t world, num_points, first_block, block_stride;
+    int scrub;
+};
+
+template <int DEG, typename AttrT>
+__global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerReduceParams p) {
+    constexpr int GR = grad_row(DEG), SR = sh_row(DEG), A = attr_dim(DEG);
+    constexpr int ROW_VECS = GR / 4;                 // float4 per accumulator row
+    constexpr int IN_VECS = kPeerRows * ROW_VECS;    // float4 loads per block (<= 208)
+    constexpr int ATTR_VECS = kPeerRows * A / 4;     // 4-element stores of the attribute block
+    constexpr int PTS_VECS = kPeerRows * 3 / 4;      // float4 stores of the points block
+    static_assert(IN_VECS <= 256 && ATTR_VECS + PTS_VECS <= 256, "one pass per block");
+    static_assert((kPeerRows * A) % 4 == 0 && (kPeerRows * 3) % 4 == 0, "blocks are whole vectors");
+    __shared__ __align__(16) float rows[kPeerRows * GR];
+    const uint32_t num_blocks = (p.num_points + kPeerRows - 1) / kPeerRows;
+    const uint32_t t = threadIdx.x;
+    for (uint32_t b = p.first_block + blockIdx.x * p.block_stride; b < num_blocks; b += gridDim.x * p.block_stride) {
+        const uint32_t row0 = b * kPeerRows;
+        const uint32_t nrows = min((uint32_t)kPeerRows, p.num_points - row0);
+        if (t < nrows * ROW_VECS) {
+            const uint64_t off = (uint64_t)row0 * GR + 4ull * t;
+            float4 v[kMaxPeers];
+#pragma unroll
+            for (int w = 0; w < kMaxPeers; ++w)
+                if (w < (int)p.world)
+                    v[w] = *reinterpret_cast<const float4 *>(p.acc[w] + off);
+            float4 s = v[0];
+#pragma unroll
+            for (int w = 1; w < kMaxPeers; ++w)
+                if (w < (int)p.world) {
+                    s.x += v[w].x;
+                    s.y += v[w].y;
+                    s.z += v[w].z;
+                    s.w += v[w].w;
+                }
+            *reinterpret_cast<float4 *>(rows + 4 * t) = s;
+        }
+        __syncthreads();
+        const bool full = nrows == kPeerRows;
+        if (t < ATTR_VECS) {
+            // four consecutive elements of the block's [rows][A] output
+            AttrT o[4];
+            bool live[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = 4 * t + k, r = e / A, c = e % A;
+                live[k] = r < nrows;
+                float x = live[k] ? rows[r * GR + (c < A - 1 ? c : SR)] : 0.0f;
+                AttrT a = (AttrT)x;
+                if (p.scrub && !isfinite((float)a))
+                    a = (AttrT)0.0f;
+                o[k] = a;
+            }
+            const uint64_t e0 = (uint64_t)row0 * A + 4ull * t;
+            for (uint32_t w = 0; w < p.world; ++w) {
+                AttrT *dst = reinterpret_cast<AttrT *>(p.attr_grad[w]) + e0;
+                if (full) {
+                    if (sizeof(AttrT) == 4)
+                        *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
+                    else
+                        *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(o);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (live[k])
+                            dst[k] = o[k];
+                }
+            }
+        } else if (t < ATTR_VECS + PTS_VECS) {
+            const uint32_t u = t - ATTR_VECS;
+            float o[4];
+            bool live[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = 4 * u + k, r = e / 3, c = e % 3;
+                live[k] = r < nrows;
+                float x = live[k] ? rows[r * GR + SR + 1 + c] : 0.0f;
+                if (p.scrub && !isfinite(x))
+                    x = 0.0f;
+                o[k] = x;
+            }
+            const uint64_t e0 = (uint64_t)row0 * 3 + 4ull * u;
+            for (uint32_t w = 0; w < p.world; ++w) {
+                float *dst = p.points_grad[w] + e0;
+                if (full) {
+                    *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (live[k])
+                            dst[k] = o[k];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

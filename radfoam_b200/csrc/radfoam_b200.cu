@@ -109,7 +109,17 @@ struct rfb_pipeline {
     DeviceBuffer cells, sh_rows, faces, nbr, acc;
     SceneKey key;
     bool key_valid = false;
+    // producer stream + completion event of the mirrors / of the tape: a consumer on another stream waits on it
+    cudaStream_t scene_stream = nullptr, tape_stream = nullptr;
+    cudaEvent_t scene_ready = nullptr, tape_ready = nullptr;
+    // RFB_DEBUG=1: checksum of (points, attributes) taken when the mirrors were built, re-checked on every cache hit
+    DeviceBuffer debug_sum;
+    uint64_t scene_checksum = 0;
     uint32_t acc_points = 0;
+    // caller-provided accumulator memory (rfb_set_grad_accumulator: a peer-mapped allocation for the fused
+    // multi-GPU reduction); nullptr = the pipeline's own `acc`
+    float *acc_external = nullptr;
+    uint64_t acc_external_floats = 0;
     // walk tape (forward records, backward replays; see foam_kernels.cuh)
     DeviceBuffer tape_pool, tape_table, tape_per_ray, tape_ctrl;
     uint32_t tape_capacity = 0;      // chunks
@@ -146,6 +156,50 @@ int check_device(rfb_pipeline *p) {
     return 0;
 }
 
+bool debug_checks() {
+    static const bool on = [] {
+        const char *e = getenv("RFB_DEBUG");
+        return e && *e && *e != '0';
+    }();
+    return on;
+}
+
+// RFB_DEBUG only (synchronises): order-independent checksum of the caller's points and attributes
+int scene_checksum(rfb_pipeline *p, uint32_t n, const float *points, const void *attrs, cudaStream_t stream,
+                   uint64_t &out) {
+    RFB_CUDA(p->debug_sum.ensure(sizeof(unsigned long long)));
+    RFB_CUDA(cudaMemsetAsync(p->debug_sum.ptr, 0, sizeof(unsigned long long), stream));
+    const int A = attr_dim(p->sh_degree);
+    const uint64_t attr_words = (uint64_t)n * A * (p->attr_dtype == RFB_FLOAT16 ? 2 : 4) / 4;
+    auto *sum = reinterpret_cast<unsigned long long *>(p->debug_sum.ptr);
+    if (n) {
+        RFB_LAUNCH((checksum_kernel), grid_for((uint64_t)n * 3, 256), 256, 0, stream,
+                   reinterpret_cast<const uint32_t *>(points), (uint64_t)n * 3, sum);
+        RFB_LAUNCH((checksum_kernel), grid_for(attr_words, 256), 256, 0, stream,
+                   reinterpret_cast<const uint32_t *>(attrs), attr_words, sum);
+    }
+    unsigned long long host = 0;
+    RFB_CUDA(cudaMemcpyAsync(&host, sum, sizeof(host), cudaMemcpyDeviceToHost, stream));
+    RFB_CUDA(cudaStreamSynchronize(stream));
+    out = host;
+    return 0;
+}
+
+// make `stream` wait for work recorded in `ev` on `producer` (no-op on the same stream)
+int wait_for(cudaEvent_t ev, cudaStream_t producer, cudaStream_t stream) {
+    if (ev && producer != stream)
+        RFB_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+    return 0;
+}
+
+int mark(cudaEvent_t &ev, cudaStream_t &producer, cudaStream_t stream) {
+    if (!ev)
+        RFB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    RFB_CUDA(cudaEventRecord(ev, stream));
+    producer = stream;
+    return 0;
+}
+
 // (Re)build the internal mirrors of the scene unless the caller vouches they are current.
 int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *attrs, uint32_t e,
                  const uint32_t *adj, const uint32_t *off, bool need_faces,
@@ -161,9 +215,21 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     k.n = n;
     k.e = e;
     k.version = opts ? opts->scene_version : 0;
-    if (p->key_valid && k.version != 0 && k == p->key && (p->key.faces || !need_faces))
-        return 0;
+    if (p->key_valid && k.version != 0 && k == p->key && (p->key.faces || !need_faces)) {
+        if (debug_checks()) {
+            uint64_t now = 0;
+            if (int rc = scene_checksum(p, n, points, attrs, stream, now))
+                return rc;
+            if (now != p->scene_checksum)
+                return fail("RFB_DEBUG: points/attributes changed but scene_version did not (stale scene mirrors; "
+                            "bump rfb_launch_opts.scene_version whenever the scene tensors are written)");
+        }
+        return wait_for(p->scene_ready, p->scene_stream, stream);
+    }
     p->key_valid = false;
+    if (debug_checks())
+        if (int rc = scene_checksum(p, n, points, attrs, stream, p->scene_checksum))
+            return rc;
 
     const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
     RFB_CUDA(p->cells.ensure((size_t)n * sizeof(float4)));
@@ -199,7 +265,7 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     k.faces = need_faces;
     p->key = k;
     p->key_valid = true;
-    return 0;
+    return mark(p->scene_ready, p->scene_stream, stream);
 }
 
 void ray_grid(uint32_t num_rays, uint32_t image_width, uint32_t &blocks, uint32_t &blocks_x,
@@ -207,8 +273,8 @@ void ray_grid(uint32_t num_rays, uint32_t image_width, uint32_t &blocks, uint32_
     width_used = (image_width && num_rays % image_width == 0) ? image_width : 0;
     if (width_used) {
         uint32_t h = num_rays / width_used;
-        blocks_x = (width_used + 15) / 16;
-        blocks = blocks_x * ((h + 7) / 8);
+        blocks_x = (width_used + kTileW - 1) / kTileW;
+        blocks = blocks_x * ((h + kTileH - 1) / kTileH);
     } else {
         blocks_x = 0;
         blocks = (num_rays + kBlock - 1) / kBlock;
@@ -252,9 +318,12 @@ int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, con
     return 0;
 }
 
-// Size / reset the tape for a recording forward of `blocks` CTAs; fills `tape`.
+// Size / reset the tape for a recording forward of `blocks` CTAs; fills `tape`.  The tape is an optimisation:
+// when its memory cannot be had (the pool is a raw cudaMalloc next to the caller's own allocator), `ok` comes
+// back false, the forward runs without recording and the backward re-walks.
 int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t max_steps, Tape &tape,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, bool &ok) {
+    ok = false;
     const uint32_t num_warps = blocks * (kBlock / 32);
     const uint32_t stride = max_steps / kTapeChunk + 2;
     // grow the pool if the previous recording needed more chunks than it had
@@ -268,10 +337,28 @@ int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t m
     if (p->tape_capacity < want)
         p->tape_capacity = (uint32_t)(want < 0xFFFFFFF0ull ? want : 0xFFFFFFF0ull);
     const size_t chunk_bytes = (size_t)kTapeChunk * 32 * sizeof(uint2);
-    RFB_CUDA(p->tape_pool.ensure((size_t)p->tape_capacity * chunk_bytes));
-    RFB_CUDA(p->tape_table.ensure((size_t)num_warps * stride * sizeof(uint32_t)));
-    RFB_CUDA(p->tape_per_ray.ensure((size_t)num_rays * sizeof(uint2)));
-    RFB_CUDA(p->tape_ctrl.ensure(4 * sizeof(uint32_t)));
+    size_t pool_bytes = (size_t)p->tape_capacity * chunk_bytes;
+    if (pool_bytes > p->tape_pool.bytes) {
+        // growing: never take more than half of what is free now (plus what the pool already holds)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t cap = (free_b + p->tape_pool.bytes) / 2;
+            if (pool_bytes + pool_bytes / 16 + 256 > cap) {
+                const uint64_t fit = cap / (chunk_bytes + chunk_bytes / 16 + 1);
+                p->tape_capacity = (uint32_t)(fit < p->tape_capacity ? fit : p->tape_capacity);
+                pool_bytes = (size_t)p->tape_capacity * chunk_bytes;
+            }
+        }
+        cudaGetLastError();
+    }
+    if (p->tape_capacity < want || p->tape_pool.ensure(pool_bytes) != cudaSuccess ||
+        p->tape_table.ensure((size_t)num_warps * stride * sizeof(uint32_t)) != cudaSuccess ||
+        p->tape_per_ray.ensure((size_t)num_rays * sizeof(uint2)) != cudaSuccess ||
+        p->tape_ctrl.ensure(4 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError(); // out of memory is not sticky; forget it
+        p->tape_capacity = 0; // start from the first guess next time
+        return 0;
+    }
     RFB_CUDA(cudaMemsetAsync(p->tape_ctrl.ptr, 0, 4 * sizeof(uint32_t), stream));
     if (!p->tape_readback) {
         RFB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->tape_readback), 4 * sizeof(uint32_t)));
@@ -284,6 +371,7 @@ int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t m
     tape.ctrl = reinterpret_cast<uint32_t *>(p->tape_ctrl.ptr);
     tape.capacity = p->tape_capacity;
     tape.table_stride = stride;
+    ok = true;
     return 0;
 }
 
@@ -426,6 +514,11 @@ void rfb_destroy_pipeline(rfb_pipeline *p) {
     for (auto &e : p->ev)
         if (e)
             cudaEventDestroy(e);
+    if (p->scene_ready)
+        cudaEventDestroy(p->scene_ready);
+    if (p->tape_ready)
+        cudaEventDestroy(p->tape_ready);
+    p->debug_sum.release();
     delete p;
 }
 
@@ -556,11 +649,11 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
     fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
     fa.off = point_adjacency_offsets;
-    const bool record = opts && (opts->flags & RFB_FLAG_RECORD_TAPE) && opts->scene_version != 0;
+    bool record = opts && (opts->flags & RFB_FLAG_RECORD_TAPE) && opts->scene_version != 0;
     p->tape_valid = false;
     Tape tape = {};
     if (record)
-        if (int rc = prepare_tape(p, blocks, num_rays, s.max_intersections, tape, stream))
+        if (int rc = prepare_tape(p, blocks, num_rays, s.max_intersections, tape, stream, record))
             return rc;
     if (int rc = profile_mark(p, 0, stream))
         return rc;
@@ -582,6 +675,8 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
         p->tape_key.weight_threshold = s.weight_threshold;
         p->tape_key.scene_version = opts->scene_version;
         p->tape_valid = true;
+        if (int rc = mark(p->tape_ready, p->tape_stream, stream))
+            return rc;
     }
     return 0;
 }
@@ -603,8 +698,15 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
         return rc;
     const int GR = grad_row(p->sh_degree);
     size_t acc_bytes = (size_t)num_points * GR * sizeof(float);
-    RFB_CUDA(p->acc.ensure(acc_bytes));
-    RFB_CUDA(cudaMemsetAsync(p->acc.ptr, 0, acc_bytes, stream));
+    float *acc_ptr = p->acc_external;
+    if (acc_ptr) {
+        if ((uint64_t)num_points * GR > p->acc_external_floats)
+            return fail("rfb_trace_backward: the accumulator given to rfb_set_grad_accumulator is too small");
+    } else {
+        RFB_CUDA(p->acc.ensure(acc_bytes));
+        acc_ptr = reinterpret_cast<float *>(p->acc.ptr);
+    }
+    RFB_CUDA(cudaMemsetAsync(acc_ptr, 0, acc_bytes, stream));
     p->acc_points = num_points;
     if (num_rays == 0)
         return 0;
@@ -629,7 +731,7 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
     bp.depth_grad = depth_grad;
     bp.ray_error = ray_error;
     bp.point_error = ray_error ? point_error : nullptr;
-    bp.acc = reinterpret_cast<float *>(p->acc.ptr);
+    bp.acc = acc_ptr;
     bp.num_rays = num_rays;
     bp.num_q = num_depth_quantiles;
     bp.weight_threshold = s.weight_threshold;
@@ -659,6 +761,8 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
         tape.ctrl = reinterpret_cast<uint32_t *>(p->tape_ctrl.ptr);
         tape.capacity = p->tape_capacity;
         tape.table_stride = p->tape_table_stride;
+        if (int rc = wait_for(p->tape_ready, p->tape_stream, stream))
+            return rc;
     }
     if (int rc = cached ? launch_backward_cached(p->sh_degree, bp, fa, tape, blocks, stream)
                         : launch_backward(p->sh_degree, bp, fa, blocks, stream))
@@ -669,8 +773,66 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
 int rfb_grad_accumulator(rfb_pipeline *p, float **ptr, uint64_t *num_floats) {
     if (!p || !ptr || !num_floats)
         return fail("rfb_grad_accumulator: NULL argument");
-    *ptr = reinterpret_cast<float *>(p->acc.ptr);
+    *ptr = p->acc_external ? p->acc_external : reinterpret_cast<float *>(p->acc.ptr);
     *num_floats = (uint64_t)p->acc_points * grad_row(p->sh_degree);
+    return 0;
+}
+
+int rfb_set_grad_accumulator(rfb_pipeline *p, float *ptr, uint64_t num_floats) {
+    if (!p)
+        return fail("rfb_set_grad_accumulator: pipeline is NULL");
+    if (ptr && (reinterpret_cast<uintptr_t>(ptr) & 15u))
+        return fail("rfb_set_grad_accumulator: the accumulator must be 16-byte aligned");
+    p->acc_external = ptr;
+    p->acc_external_floats = ptr ? num_floats : 0;
+    p->acc_points = 0;
+    return 0;
+}
+
+int rfb_reduce_finalize_peers(rfb_pipeline *p, uint32_t world, uint32_t rank, uint32_t num_points,
+                              const float *const *peer_acc, void *const *peer_attribute_grad,
+                              float *const *peer_points_grad, uint32_t flags, void *stream_) {
+    if (!p || !peer_acc || !peer_attribute_grad || !peer_points_grad)
+        return fail("rfb_reduce_finalize_peers: NULL argument");
+    if (world == 0 || world > (uint32_t)kMaxPeers || rank >= world)
+        return fail("rfb_reduce_finalize_peers: world must be 1.." + std::to_string(kMaxPeers) + " and rank < world");
+    if (num_points == 0)
+        return 0;
+    PeerReduceParams pr;
+    for (uint32_t w = 0; w < world; ++w) {
+        if (!peer_acc[w] || !peer_attribute_grad[w] || !peer_points_grad[w])
+            return fail("rfb_reduce_finalize_peers: NULL peer pointer");
+        if ((reinterpret_cast<uintptr_t>(peer_acc[w]) | reinterpret_cast<uintptr_t>(peer_attribute_grad[w]) |
+             reinterpret_cast<uintptr_t>(peer_points_grad[w])) & 15u)
+            return fail("rfb_reduce_finalize_peers: peer arrays must be 16-byte aligned");
+        pr.acc[w] = peer_acc[w];
+        pr.attr_grad[w] = peer_attribute_grad[w];
+        pr.points_grad[w] = peer_points_grad[w];
+    }
+    pr.world = world;
+    pr.num_points = num_points;
+    // this rank's share: whole blocks of kPeerRows rows, dealt round-robin so that every rank streams from
+    // the whole array (no rank's HBM serves one reader only)
+    const uint32_t num_blocks = (num_points + kPeerRows - 1) / kPeerRows;
+    pr.first_block = rank;
+    pr.block_stride = world;
+    pr.scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
+    const uint32_t mine = (num_blocks + world - 1 - rank) / world;
+    if (mine == 0)
+        return 0;
+    int grid = (int)(mine < 148u * 8u ? mine : 148u * 8u);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (p->sh_degree * 2 + (p->attr_dtype == RFB_FLOAT16 ? 1 : 0)) {
+    case 0: RFB_LAUNCH((reduce_finalize_peers_kernel<0, float>), grid, 256, 0, stream, pr); break;
+    case 1: RFB_LAUNCH((reduce_finalize_peers_kernel<0, __half>), grid, 256, 0, stream, pr); break;
+    case 2: RFB_LAUNCH((reduce_finalize_peers_kernel<1, float>), grid, 256, 0, stream, pr); break;
+    case 3: RFB_LAUNCH((reduce_finalize_peers_kernel<1, __half>), grid, 256, 0, stream, pr); break;
+    case 4: RFB_LAUNCH((reduce_finalize_peers_kernel<2, float>), grid, 256, 0, stream, pr); break;
+    case 5: RFB_LAUNCH((reduce_finalize_peers_kernel<2, __half>), grid, 256, 0, stream, pr); break;
+    case 6: RFB_LAUNCH((reduce_finalize_peers_kernel<3, float>), grid, 256, 0, stream, pr); break;
+    default: RFB_LAUNCH((reduce_finalize_peers_kernel<3, __half>), grid, 256, 0, stream, pr); break;
+    }
+    RFB_LAUNCHED();
     return 0;
 }
 
@@ -688,13 +850,12 @@ int rfb_trace_backward_finalize(rfb_pipeline *p, uint32_t num_points, float *poi
     const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
     int grid = grid_for((uint64_t)num_points * 32, 256);
     int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
+    const float *acc_ptr = p->acc_external ? p->acc_external : reinterpret_cast<const float *>(p->acc.ptr);
     if (p->attr_dtype == RFB_FLOAT16)
-        RFB_LAUNCH((finalize_grads_kernel<__half>), grid, 256, 0, stream,
-                   reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
+        RFB_LAUNCH((finalize_grads_kernel<__half>), grid, 256, 0, stream, acc_ptr, num_points, A, SR, points_grad,
                    reinterpret_cast<__half *>(attribute_grad), scrub);
     else
-        RFB_LAUNCH((finalize_grads_kernel<float>), grid, 256, 0, stream,
-                   reinterpret_cast<const float *>(p->acc.ptr), num_points, A, SR, points_grad,
+        RFB_LAUNCH((finalize_grads_kernel<float>), grid, 256, 0, stream, acc_ptr, num_points, A, SR, points_grad,
                    reinterpret_cast<float *>(attribute_grad), scrub);
     RFB_LAUNCHED();
     return 0;
@@ -774,8 +935,8 @@ int rfb_trace_benchmark(rfb_pipeline *p, const rfb_trace_settings *settings, uin
     bp.cam.model = camera->model;
     bp.weight_threshold = s.weight_threshold;
     bp.max_steps = s.max_intersections;
-    bp.blocks_x = (camera->width + 15) / 16;
-    uint32_t blocks = bp.blocks_x * ((camera->height + 7) / 8);
+    bp.blocks_x = (camera->width + kTileW - 1) / kTileW;
+    uint32_t blocks = bp.blocks_x * ((camera->height + kTileH - 1) / kTileH);
     // the caller's offsets, re-laid-out (copied, not recomputed) into the padded face rows
     PaddedFaces fa;
     fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);

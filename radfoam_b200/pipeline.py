@@ -64,6 +64,7 @@ class Pipeline:
         # set by the autograd ops around their forward: was autograd recording when the op was applied?
         # (inside Function.forward grad mode is always off; None = not called through such an op)
         self.autograd_recording = None
+        self._external_acc = None  # keeps a caller-provided accumulator alive (set_grad_accumulator)
         # unordered ray batches ([R, 6], the reference's training batches: train.py:61) are traced
         # in a coherent order -- sorted by (start cell, direction) -- and the per-ray outputs are
         # scattered back; results are unchanged, neighbouring lanes share cells again
@@ -499,6 +500,28 @@ class Pipeline:
         if n == 0:
             return torch.empty((0, row), dtype=torch.float32, device=device)
         return _wrap_device_memory(ptr.value, (n, row), device)
+
+    def set_grad_accumulator(self, acc) -> None:
+        """Scatter the backward into caller-provided memory (an ``[N, grad_row_floats]`` float32 CUDA tensor the
+        caller keeps alive, e.g. symmetric memory the other GPUs can address); ``None`` = the pipeline's own."""
+        if acc is None:
+            self._external_acc = None
+            _lib.check(self._lib.rfb_set_grad_accumulator(self._handle, None, 0))
+            return
+        if acc.dtype != torch.float32 or acc.device.type != "cuda" or not acc.is_contiguous():
+            raise RuntimeError("the accumulator must be a contiguous float32 CUDA tensor")
+        self._external_acc = acc
+        _lib.check(self._lib.rfb_set_grad_accumulator(self._handle, acc.data_ptr(), acc.numel()))
+
+    def reduce_finalize_peers(self, world, rank, num_points, peer_acc, peer_attr_grad, peer_points_grad, device,
+                              scrub_nonfinite=False):
+        """``rfb_reduce_finalize_peers``: the pointer tables are ctypes ``c_void_p`` arrays of ``world`` device
+        addresses valid on this device.  The caller provides the cross-GPU barriers around it."""
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(self._lib.rfb_reduce_finalize_peers(
+                self._handle, world, rank, num_points, peer_acc, peer_attr_grad, peer_points_grad,
+                _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, stream))
 
     def trace_backward_finalize(self, num_points, device, scrub_nonfinite=False):
         attr_grad = torch.empty((num_points, self._attr_dim), dtype=self._dtype, device=device)

@@ -10,16 +10,19 @@ replicated on every rank; rays are dealt to ranks
     shard is still a row-major image, so the kernels' 8x4 warp tiles stay coherent;
   * unordered batches ``[R, 6]``: as contiguous chunks.
 
-Forward needs no collective (disjoint pixels).  Backward scatter-adds into the pipeline's
-fp32 accumulator ``[N, grad_row]`` on each rank; ONE all-reduce (sum) of that accumulator
-makes every rank hold the full per-point gradient, then the epilogue writes the reference
-layout and zeroes non-finite entries -- after the reduction, as radfoam_model/render.py:98-99
-does after its single-GPU kernel.
+Forward needs no collective (disjoint pixels).  Backward scatter-adds into an fp32
+accumulator ``[N, grad_row]`` on each rank; ONE exchange step sums it over the ranks and writes
+the reference-layout gradients (non-finite entries zeroed AFTER the sum, as
+radfoam_model/render.py:98-99 does after its single-GPU kernel):
+a fused peer-memory kernel over NVLink where available, else an NCCL all-reduce + finalize.
 
 The partition / reassembly helpers are pure index arithmetic on torch tensors and are
 exercised on CPU with gloo (tests/test_sharded_gloo.py).
 """
 from __future__ import annotations
+
+import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -65,10 +68,17 @@ class ShardedTracer:
 
     ``trace_forward`` / ``trace_backward`` take THIS RANK'S shard of the rays (see
     :func:`shard_image` / :func:`shard_flat`) and the full, replicated scene; backward
-    returns the full (all-reduced) gradients on every rank.
+    returns the full (reduced) gradients on every rank.
+
+    The exchange step.  Default on NCCL/CUDA: ONE kernel per rank that sums the peers' accumulators over
+    NVLink, finalizes and stores the result into every rank's output arrays
+    (``rfb_reduce_finalize_peers``; the buffers live in torch symmetric memory, the two cross-GPU barriers
+    are its signal-pad barriers).  Fallback (CPU/gloo, no peer access, ``fused_reduce=False`` or
+    ``RFB_FUSED_REDUCE=0``): ``all_reduce`` of the accumulator, then the local finalize kernel.
+    All ranks agree on the path (a MIN all-reduce of the set-up outcome).
     """
 
-    def __init__(self, pipeline, group=None, band: int = 8):
+    def __init__(self, pipeline, group=None, band: int = 8, fused_reduce: bool | None = None):
         self.pipeline = pipeline
         self.group = group
         self.band = band
@@ -77,6 +87,11 @@ class ShardedTracer:
             self.world = dist.get_world_size(group)
         else:
             self.rank, self.world = 0, 1
+        if fused_reduce is None:
+            fused_reduce = os.environ.get("RFB_FUSED_REDUCE", "1") != "0"
+        self.fused_reduce = fused_reduce
+        self._peer = None          # set-up state of the fused path; False = tried and unavailable
+        self.fused_reduce_error = None
 
     # -- partition helpers bound to this rank
     def shard(self, t: torch.Tensor, image: bool) -> torch.Tensor:
@@ -97,6 +112,79 @@ class ShardedTracer:
         dist.all_gather(parts, padded.contiguous(), group=self.group)
         return unshard_image([p[:s] for p, s in zip(parts, sizes)], height, self.band)
 
+    # -- the exchange step
+    def reduction_name(self) -> str:
+        if self.world == 1:
+            return "no collective"
+        if self._peer:
+            return "one fused peer-memory reduce+finalize kernel per rank (NVLink, symmetric memory)"
+        return "one NCCL all-reduce"
+
+    def _peer_setup(self, num_points: int, device):
+        """Symmetric buffers [accumulator | attr_grad | points_grad] + peer pointer tables, once per size."""
+        st = self._peer
+        if st is False or (st and st["num_points"] == num_points):
+            return st
+        pipe = self.pipeline
+        ok, err, st = True, None, None
+        try:
+            if not (self.fused_reduce and device.type == "cuda" and dist.get_backend(self.group) == "nccl"
+                    and hasattr(pipe, "set_grad_accumulator")):
+                raise RuntimeError("fused reduction needs CUDA + NCCL and a radfoam_b200.Pipeline")
+            import torch.distributed._symmetric_memory as symm
+
+            gr, adim = pipe.grad_row_floats(), pipe.attribute_dim()
+            half = pipe.attribute_type() == torch.float16
+            acc_f = num_points * gr
+            attr_f = (num_points * adim * (2 if half else 4) + 15) // 16 * 4   # floats, 16-byte granules
+            pts_f = (num_points * 3 + 3) // 4 * 4
+            group = self.group if self.group is not None else dist.group.WORLD
+            enable = getattr(symm, "enable_symm_mem_for_group", None)
+            if enable is not None:
+                try:
+                    enable(group.group_name)
+                except Exception:  # noqa: BLE001  (deprecated no-op in newer torch)
+                    pass
+            buf = symm.empty(acc_f + attr_f + pts_f, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, group)
+            bases = [int(p) for p in hdl.buffer_ptrs]
+            arr = lambda off: (ctypes.c_void_p * self.world)(*[b + 4 * off for b in bases])  # noqa: E731
+            attr_view = buf[acc_f:acc_f + attr_f]
+            attr_view = (attr_view.view(torch.float16) if half else attr_view)[:num_points * adim].view(num_points, adim)
+            st = dict(num_points=num_points, buf=buf, hdl=hdl, acc=buf[:acc_f].view(num_points, gr),
+                      attr=attr_view, pts=buf[acc_f + attr_f:acc_f + attr_f + num_points * 3].view(num_points, 3),
+                      peer_acc=arr(0), peer_attr=arr(acc_f), peer_pts=arr(acc_f + attr_f))
+        except Exception as e:  # noqa: BLE001
+            ok, err = False, repr(e)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.fused_reduce_error = err or "another rank could not set up symmetric memory"
+            if self._peer:
+                self.pipeline.set_grad_accumulator(None)
+            self._peer = False
+            return False
+        self._peer = st
+        pipe.set_grad_accumulator(st["acc"])
+        return st
+
+    def reduce_and_finalize(self, num_points: int, device, scrub_nonfinite: bool = True, acc=None):
+        """After ``trace_backward_accumulate`` on every rank (``acc`` = what it returned): ``(points_grad,
+        attr_grad)`` summed over the ranks."""
+        pipe = self.pipeline
+        if self.world == 1:
+            return pipe.trace_backward_finalize(num_points, device, scrub_nonfinite=scrub_nonfinite)
+        st = self._peer
+        if st:
+            st["hdl"].barrier(channel=0)   # every rank's accumulator is complete
+            pipe.reduce_finalize_peers(self.world, self.rank, num_points, st["peer_acc"], st["peer_attr"],
+                                       st["peer_pts"], device, scrub_nonfinite=scrub_nonfinite)
+            st["hdl"].barrier(channel=1)   # every rank's stores have landed; accumulators may be reused
+            return st["pts"].clone(), st["attr"].clone()
+        dist.all_reduce(acc if acc is not None else pipe.grad_accumulator(device), op=dist.ReduceOp.SUM,
+                        group=self.group)
+        return pipe.trace_backward_finalize(num_points, device, scrub_nonfinite=scrub_nonfinite)
+
     # -- the hot path
     def trace_forward(self, *args, **kwargs):
         return self.pipeline.trace_forward(*args, **kwargs)
@@ -110,16 +198,16 @@ class ShardedTracer:
                 points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point,
                 rgb_out, grad_in, depth_quantiles, depth_indices, depth_grad_in, ray_error,
                 weight_threshold, max_intersections, scrub_nonfinite=scrub_nonfinite)
+        if self._peer is None or (self._peer and self._peer["num_points"] != points.shape[0]):
+            self._peer_setup(points.shape[0], rays.device)
         acc, point_error = self.pipeline.trace_backward_accumulate(
             points, attributes, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out,
             grad_in, depth_quantiles, depth_indices, depth_grad_in, ray_error, weight_threshold,
             max_intersections)
-        # the single collective of the path: per-point gradient sum over ranks
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        # the single exchange step of the path: per-point gradient sum over ranks
+        points_grad, attr_grad = self.reduce_and_finalize(points.shape[0], rays.device, scrub_nonfinite, acc)
         if point_error is not None:
             dist.all_reduce(point_error, op=dist.ReduceOp.SUM, group=self.group)
-        points_grad, attr_grad = self.pipeline.trace_backward_finalize(
-            points.shape[0], rays.device, scrub_nonfinite=scrub_nonfinite)
         out = {"points_grad": points_grad, "attr_grad": attr_grad, "ray_grad": torch.empty_like(rays)}
         if point_error is not None:
             out["point_error"] = point_error

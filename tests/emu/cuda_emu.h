@@ -372,6 +372,9 @@ inline __half atomicAdd(__half *p, __half v) {
     }
 }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
 inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline void rfb_emu_red_add_v4(float *p, float a, float b, float c, float d) {
     emu::counters.red_v4.fetch_add(1, std::memory_order_relaxed);
@@ -453,6 +456,8 @@ inline T __shfl_down_sync(unsigned mask, T value, unsigned delta, int width = 32
 #define cudaMemsetAsync(p, v, n, s) (std::memset((p), (v), (n)), cudaSuccess)
 #define cudaMemcpyAsync(d, s, n, kind, st) (std::memcpy((d), (s), (n)), cudaSuccess)
 #define cudaStreamSynchronize(s) (cudaSuccess)
+#define cudaStreamWaitEvent(s, e, f) (cudaSuccess)
+#define cudaMemGetInfo(f, t) (*(f) = (size_t)1 << 40, *(t) = (size_t)1 << 40, cudaSuccess)
 #define cudaGetLastError() (cudaSuccess)
 #define cudaGetErrorString(e) ("emulated CUDA runtime error")
 #define cudaGetDevice(p) (*(p) = 0, cudaSuccess)

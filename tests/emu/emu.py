@@ -173,6 +173,20 @@ class EmuPipeline:
             product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
         return out
 
+    def reduce_finalize_peers(self, rank, accumulators, scrub_nonfinite=False):
+        """rfb_reduce_finalize_peers with `accumulators` (one [N, grad_row] float32 array per rank) standing in for
+        the peer-mapped buffers; returns THIS rank's writes into every rank's outputs as (attr_grads, points_grads),
+        lists of arrays pre-filled with a sentinel so that the rows a rank does not own are recognisable."""
+        world, n = len(accumulators), accumulators[0].shape[0]
+        accs = [_c(a, np.float32) for a in accumulators]
+        attr = [np.full((n, self.attr_dim), 7.0, self.dtype) for _ in range(world)]
+        pts = [np.full((n, 3), 7.0, np.float32) for _ in range(world)]
+        table = lambda arrs: (ctypes.c_void_p * world)(*[a.ctypes.data for a in arrs])  # noqa: E731
+        _check(self.lib.rfb_reduce_finalize_peers(
+            self.handle, world, rank, n, table(accs), table(attr), table(pts),
+            product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
+        return attr, pts
+
     def trace_benchmark(self, points, attributes, adjacency, offsets, adjacent_diff, camera, start_point,
                         weight_threshold=None, max_intersections=None, scene_version=0):
         pts, att, adj, off = self._scene(points, attributes, adjacency, offsets)

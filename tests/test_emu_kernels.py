@@ -252,6 +252,45 @@ print("ok")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("world,num_points,deg,dtype", [(2, 64, 3, np.float32), (3, 45, 3, np.float32),
+                                                        (8, 150, 3, np.float32), (2, 37, 1, np.float16),
+                                                        (4, 16, 0, np.float32), (5, 3, 2, np.float16)])
+def test_fused_peer_reduce_finalize(world, num_points, deg, dtype):
+    """The multi-GPU exchange kernel (rfb_reduce_finalize_peers) on the CPU: every rank sums its row blocks over all
+    ranks' accumulators in rank order, finalizes, and writes them into every rank's outputs; after all ranks ran,
+    every rank holds exactly what all-reduce + finalize gives (ragged last block, fp16 outputs, scrub)."""
+    rng = np.random.default_rng(world * 1000 + num_points)
+    pipe = emu.EmuPipeline(deg, dtype)
+    sr = ((3 * (deg + 1) ** 2 + 3) // 4) * 4
+    gr, adim = sr + 4, 1 + 3 * (deg + 1) ** 2
+    accs = [rng.normal(size=(num_points, gr)).astype(np.float32) for _ in range(world)]
+    accs[0][1, 2] = np.inf          # becomes non-finite in the sum -> scrubbed
+    accs[-1][num_points - 1, sr + 2] = np.nan
+    total = accs[0].copy()
+    for a in accs[1:]:              # rank order, float32: bit-exact expectation
+        total = total + a
+    want_attr = np.concatenate([total[:, :adim - 1], total[:, sr:sr + 1]], axis=1).astype(dtype)
+    want_pts = total[:, sr + 1:sr + 4].copy()
+    want_attr[~np.isfinite(want_attr.astype(np.float32))] = 0
+    want_pts[~np.isfinite(want_pts)] = 0
+    got_attr = [np.full((num_points, adim), 7.0, dtype) for _ in range(world)]
+    got_pts = [np.full((num_points, 3), 7.0, np.float32) for _ in range(world)]
+    written = np.zeros(num_points, dtype=np.int64)
+    for rank in range(world):
+        attr, pts = pipe.reduce_finalize_peers(rank, accs, scrub_nonfinite=True)
+        mine = (np.arange(num_points) // 16) % world == rank      # blocks of 16 rows, round-robin
+        for w in range(world):
+            assert np.all(attr[w][~mine] == 7.0) and np.all(pts[w][~mine] == 7.0)   # nothing outside its share
+            got_attr[w][mine] = attr[w][mine]
+            got_pts[w][mine] = pts[w][mine]
+        written += mine
+    assert np.all(written == 1)
+    for w in range(world):
+        assert np.array_equal(got_attr[w].view(np.uint16 if dtype == np.float16 else np.uint32),
+                              want_attr.view(np.uint16 if dtype == np.float16 else np.uint32))
+        assert np.array_equal(got_pts[w].view(np.uint32), want_pts.view(np.uint32))
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_ray_sharded_split_backward_matches_single_rank(world, long_walk_scene):
     """The multi-GPU data path on the CPU: the frame is dealt to `world` ranks as interleaved 8-row bands

@@ -20,7 +20,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, results):
+def _worker(rank, world, port, fused, results):
     import torch
     import torch.distributed as dist
 
@@ -37,7 +37,7 @@ def _worker(rank, world, port, results):
         dev = torch.device("cuda", rank)
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
         scene = [d(x) for x in (f.points, f.attributes, f.adjacency, f.offsets)]
-        tracer = sharded.ShardedTracer(radfoam_b200.create_pipeline(3))
+        tracer = sharded.ShardedTracer(radfoam_b200.create_pipeline(3), fused_reduce=fused)
         full = {k: d(v) for k, v in dict(rays=case.rays, start=case.start, dq=case.quantiles,
                                          g=case.grad_rgba, gd=case.grad_depth).items()}
         mine = {k: tracer.shard(v, image=True).contiguous() for k, v in full.items()}
@@ -45,10 +45,18 @@ def _worker(rank, world, port, results):
         H = case.rays.shape[0]
         rgba = tracer.gather_image(fwd["rgba"], H)
         nint = tracer.gather_image(fwd["num_intersections"].to(torch.int32), H)
-        bwd = tracer.trace_backward(*scene, mine["rays"], mine["start"], fwd["rgba"], mine["g"], mine["dq"],
-                                    fwd["depth_indices"], mine["gd"], scrub_nonfinite=False)
+        for _ in range(2):  # twice: the second step re-uses (and re-zeroes) the peer-mapped accumulators
+            bwd = tracer.trace_backward(*scene, mine["rays"], mine["start"], fwd["rgba"], mine["g"], mine["dq"],
+                                        fwd["depth_indices"], mine["gd"], scrub_nonfinite=False)
         torch.cuda.synchronize()
+        # every rank must hold the same bits
+        mine_bits = torch.cat([bwd["points_grad"].reshape(-1), bwd["attr_grad"].reshape(-1)]).view(torch.int32)
+        all_bits = [torch.empty_like(mine_bits) for _ in range(world)]
+        dist.all_gather(all_bits, mine_bits)
         if rank == 0:
+            results["same_on_all_ranks"] = bool(all(torch.equal(all_bits[0], b) for b in all_bits))
+            results["fused_active"] = bool(tracer._peer)
+            results["fused_error"] = tracer.fused_reduce_error
             single = radfoam_b200.create_pipeline(3)
             sf = single.trace_forward(*scene, full["rays"], full["start"], depth_quantiles=full["dq"])
             sb = single.trace_backward(*scene, full["rays"], full["start"], sf["rgba"], full["g"], full["dq"],
@@ -63,7 +71,8 @@ def _worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_matches_single_gpu():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_peer_kernel", "nccl_all_reduce"])
+def test_two_gpu_sharded_matches_single_gpu(fused):
     import torch
     import torch.multiprocessing as mp
 
@@ -72,7 +81,10 @@ def test_two_gpu_sharded_matches_single_gpu():
     world = 2
     with mp.Manager() as manager:
         results = manager.dict()
-        mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), fused, results), nprocs=world, join=True)
         results = dict(results)
+    print("fused path active:", results["fused_active"], results["fused_error"])
+    assert results["fused_active"] == fused or (fused and results["fused_error"])  # falls back only with a reason
+    assert results["same_on_all_ranks"]
     assert results["rgba_equal"] and results["nint_equal"]     # same per-ray code: bit-identical
     assert results["points_grad"] < 1e-5 and results["attr_grad"] < 1e-5  # fp32 summation order only
