@@ -139,12 +139,21 @@ int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points,
                                const uint32_t *point_adjacency_offsets,
                                void *adjacent_diff, void *stream);
 
-/* Entry cell of each query point = index of its nearest point (exact, brute force; ties -> lowest
- * index).  Stands in for radfoam::nn over the AABB tree (src/aabb_tree/aabb_tree.h:18-27) for the
- * one use the tracer has for it: the start cell of a camera (radfoam_model/scene.py:224-234).
- * points[N][3], queries[M][3] f32, indices[M] u32, all device pointers. */
+/* Entry cell of each query point = index of its nearest point (exact: smallest distance, ties -> lowest index;
+ * UINT32_MAX for a query with NaN coordinates).  Stands in for radfoam::nn over the AABB tree
+ * (src/aabb_tree/aabb_tree.h:18-27) for the one use the tracer has for it: the start cell of a camera
+ * (radfoam_model/scene.py:224-234).  A tiled brute force: U x N distance evaluations, 12 N bytes of traffic in
+ * total; meant for camera counts (1 .. a few thousand queries).  points[N][3], queries[M][3] f32, indices[M]
+ * u32, all device pointers. */
 int rfb_nearest_point(const float *points, uint32_t num_points, const float *queries,
                       uint32_t num_queries, uint32_t *indices, void *stream);
+
+/* RadFoamScene.get_starting_point (radfoam_model/scene.py:224-234) in one call, without its torch.unique
+ * sort over all rays and without a host round trip: start_point_index[r] = nearest point of the origin of
+ * rays[r] (rays[R][6] f32).  Distinct origins are found with a device-side hash set, each is looked up once.
+ * Cost O(R + U N) for U distinct origins. */
+int rfb_start_points(const float *points, uint32_t num_points, const float *rays,
+                     uint32_t num_rays, uint32_t *start_point_index, void *stream);
 
 /* Per point i: indices[i] = the adjacent point farthest from it (first maximum in row order; UINT32_MAX when
  * the row is empty or every neighbour coincides with it), cell_radius[i] = sum(0.5*|p_j - p_i|) / num_faces
@@ -203,6 +212,27 @@ uint32_t rfb_grad_row_floats(const rfb_pipeline *pipeline);
 int rfb_trace_backward_finalize(rfb_pipeline *pipeline, uint32_t num_points,
                                 float *points_grad, void *attribute_grad,
                                 uint32_t flags, void *stream);
+
+/* ---- parameter-form scene: RadFoamScene.get_trace_data (radfoam_model/scene.py:202-217) fused in ----
+ * The reference builds  attributes = cat(att_dc, att_sh, activation_scale * softplus(density, beta=10)).to(dtype)
+ * with torch ops before every trace and splits attr_grad back through them afterwards (3-5 passes over [N][A]).
+ * While a parameter-form scene is bound, the `attributes` argument of rfb_trace_forward /
+ * rfb_trace_backward_accumulate is ignored (may be NULL): the re-layout kernel reads the three parameter
+ * arrays (f32: att_dc[N][3], att_sh[N][A-4], density[N] pre-activation) directly, and
+ * rfb_trace_backward_finalize_params writes the gradients of the PARAMETERS (attribute gradient rounded to the
+ * pipeline's attr dtype and scrubbed like attribute_grad, then chained through cat and softplus).  The same
+ * scene_version contract applies (bump it when the parameters are written).  rfb_trace_backward (the fused
+ * accumulate+finalize) is not available while bound. */
+typedef struct rfb_scene_params {
+    const float *att_dc;
+    const float *att_sh;
+    const float *density;
+    float activation_scale;
+} rfb_scene_params;
+int rfb_bind_scene_params(rfb_pipeline *pipeline, const rfb_scene_params *params /* NULL: unbind */);
+int rfb_trace_backward_finalize_params(rfb_pipeline *pipeline, uint32_t num_points, float *points_grad,
+                                       float *att_dc_grad, float *att_sh_grad, float *density_grad,
+                                       uint32_t flags, void *stream);
 
 /* ---- fused cross-GPU reduction + finalize over peer-mapped memory (NVLink / NVSwitch) ----
  * rfb_set_grad_accumulator: make rfb_trace_backward_accumulate scatter into caller-provided device memory

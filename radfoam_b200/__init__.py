@@ -13,7 +13,7 @@ no CPU fallback).
 """
 from . import foam  # noqa: F401  (numpy/scipy only)
 
-__all__ = ["create_pipeline", "Pipeline", "TraceRays", "ShardedTracer", "nearest_point", "starting_points",
+__all__ = ["create_pipeline", "Pipeline", "TraceRays", "TraceRaysParams", "ShardedTracer", "nearest_point", "starting_points",
            "farthest_neighbor", "foam", "library_path"]
 
 
@@ -21,9 +21,9 @@ def __getattr__(name):
     if name in ("create_pipeline", "Pipeline", "nearest_point", "starting_points", "farthest_neighbor"):
         from . import pipeline as _p
         return getattr(_p, name)
-    if name == "TraceRays":
+    if name in ("TraceRays", "TraceRaysParams"):
         from . import render as _r
-        return _r.TraceRays
+        return getattr(_r, name)
     if name == "ShardedTracer":
         from . import sharded as _s
         return _s.ShardedTracer

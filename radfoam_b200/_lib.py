@@ -28,6 +28,10 @@ class Camera(ctypes.Structure):  # rfb_camera
                 ("model", c_int32)]
 
 
+class SceneParams(ctypes.Structure):  # rfb_scene_params
+    _fields_ = [("att_dc", c_void_p), ("att_sh", c_void_p), ("density", c_void_p), ("activation_scale", c_float)]
+
+
 class LaunchOpts(ctypes.Structure):  # rfb_launch_opts
     _fields_ = [("scene_version", c_uint64), ("image_width", c_uint32), ("flags", c_uint32)]
 
@@ -47,6 +51,7 @@ SIGNATURES = {
     "rfb_attribute_type": (c_int, [_P]),
     "rfb_prefetch_adjacent_diff": (c_int, [_P, c_uint32, c_uint32, _P, _P, _P, _P]),
     "rfb_nearest_point": (c_int, [_P, c_uint32, _P, c_uint32, _P, _P]),
+    "rfb_start_points": (c_int, [_P, c_uint32, _P, c_uint32, _P, _P]),
     "rfb_farthest_neighbor": (c_int, [_P, c_uint32, _P, _P, _P, _P, _P]),
     "rfb_trace_forward": (c_int, [_P, POINTER(TraceSettings), c_uint32, _P, _P, c_uint32, _P, _P,
                                   c_uint32, _P, _P, c_uint32, _P, _P, _P, _P, _P, _P,
@@ -60,6 +65,8 @@ SIGNATURES = {
     "rfb_grad_accumulator": (c_int, [_P, POINTER(_P), POINTER(c_uint64)]),
     "rfb_grad_row_floats": (c_uint32, [_P]),
     "rfb_trace_backward_finalize": (c_int, [_P, c_uint32, _P, _P, c_uint32, _P]),
+    "rfb_bind_scene_params": (c_int, [_P, POINTER(SceneParams)]),
+    "rfb_trace_backward_finalize_params": (c_int, [_P, c_uint32, _P, _P, _P, _P, c_uint32, _P]),
     "rfb_set_grad_accumulator": (c_int, [_P, _P, c_uint64]),
     "rfb_reduce_finalize_peers": (c_int, [_P, c_uint32, c_uint32, c_uint32, POINTER(_P), POINTER(_P), POINTER(_P),
                                           c_uint32, _P]),

@@ -29,6 +29,49 @@ __global__ void build_cells_kernel(const float *__restrict__ points,
     }
 }
 
+// F.softplus(x, beta=10) and its derivative exactly as torch evaluates them on CUDA (softplus_kernel /
+// softplus_backward_kernel: threshold 20 on x*beta; log1p(exp(.)) / beta;  z / (z + 1) with z = exp(x*beta)).
+__device__ __forceinline__ float softplus_beta10(float x) {
+    const float xb = x * 10.0f;
+    return xb > 20.0f ? x : log1pf(expf(xb)) / 10.0f;
+}
+__device__ __forceinline__ float softplus_beta10_backward(float grad_out, float x) {
+    const float xb = x * 10.0f;
+    if (xb > 20.0f)
+        return grad_out;
+    const float z = expf(xb);
+    return (grad_out * z) / (z + 1.0f);
+}
+
+// The re-layout straight from the model's parameters -- RadFoamScene.get_trace_data (scene.py:202-217) fused in:
+//   attributes = cat(att_dc, att_sh, activation_scale * softplus(density, beta=10)).to(attr_dtype)
+// is never materialised; the cast is applied per value (AttrT = __half: round to fp16, then widen).
+template <typename AttrT>
+__global__ void build_cells_params_kernel(const float *__restrict__ points, const float *__restrict__ att_dc,
+                                          const float *__restrict__ att_sh, const float *__restrict__ density,
+                                          float activation_scale, uint32_t num_points, int attr_dim_, int sh_row_,
+                                          float4 *__restrict__ cells, float *__restrict__ sh_rows) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const int rest = attr_dim_ - 4; // columns of att_sh
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < num_points; i += warps) {
+        float *dst = sh_rows + (uint64_t)i * sh_row_;
+        for (int s = lane; s < sh_row_; s += 32) {
+            float v = 0.0f;
+            if (s < 3)
+                v = att_dc[3 * (uint64_t)i + s];
+            else if (s < attr_dim_ - 1)
+                v = att_sh[(uint64_t)i * rest + (s - 3)];
+            dst[s] = (float)(AttrT)v;
+        }
+        if (lane == 0) {
+            const float sigma = activation_scale * softplus_beta10(density[i]);
+            cells[i] = make_float4(points[3 * (uint64_t)i], points[3 * (uint64_t)i + 1], points[3 * (uint64_t)i + 2],
+                                   (float)(AttrT)sigma);
+        }
+    }
+}
+
 // faces[padded_begin(i) + f] = half4(RN(points[adj[e]] - points[i]), 0),
 // nbr[...] = adj[e]  (the reference's prefetch_adjacent_diff_kernel,
 // pipeline.cu:546-568, writes the same values in CSR order).  16 lanes per row.
@@ -788,6 +831,42 @@ __global__ void finalize_grads_kernel(const float *__restrict__ acc, uint32_t nu
     }
 }
 
+// accumulator -> gradients of the model's PARAMETERS (the backward of get_trace_data fused in): the attribute
+// gradient is rounded to the attribute dtype and scrubbed exactly like attr_grad above, then split into
+// att_dc / att_sh and chained through activation_scale * softplus(density, beta=10).
+template <typename AttrT>
+__global__ void finalize_params_kernel(const float *__restrict__ acc, const float *__restrict__ density,
+                                       float activation_scale, uint32_t num_points, int attr_dim_, int sh_row_,
+                                       float *__restrict__ points_grad, float *__restrict__ att_dc_grad,
+                                       float *__restrict__ att_sh_grad, float *__restrict__ density_grad, int scrub) {
+    const int gr = sh_row_ + 4;
+    const int rest = attr_dim_ - 4;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < num_points; i += warps) {
+        const float *row = acc + (uint64_t)i * gr;
+        for (int s = lane; s < attr_dim_; s += 32) {
+            float v = (s < attr_dim_ - 1) ? row[s] : row[sh_row_];
+            AttrT o = (AttrT)v;
+            if (scrub && !isfinite((float)o))
+                o = (AttrT)0.0f;
+            const float g = (float)o;
+            if (s < 3)
+                att_dc_grad[3 * (uint64_t)i + s] = g;
+            else if (s < attr_dim_ - 1)
+                att_sh_grad[(uint64_t)i * rest + (s - 3)] = g;
+            else
+                density_grad[i] = softplus_beta10_backward(g * activation_scale, density[i]);
+        }
+        if (lane < 3) {
+            float gq = row[sh_row_ + 1 + lane];
+            if (scrub && !isfinite(gq))
+                gq = 0.0f;
+            points_grad[3 * (uint64_t)i + lane] = gq;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ multi-GPU: fused reduce + finalize
 // The one exchange step of the ray-sharded path: every rank holds a partial gradient
 // accumulator [N][grad_row]; every rank needs the summed gradients in the reference layout.  Instead of
@@ -909,54 +988,122 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
 }
 
 // ------------------------------------------------------------------ entry cell
-// Nearest point of each query = the Voronoi cell that contains it = the cell a ray from that
-// origin starts in (what scene.py:224-234 gets from radfoam.nn over the AABB tree,
-// aabb_tree.cu:343-415).  A camera origin is shared by every ray of a frame (and a training
-// batch has a few hundred distinct origins), so an exact brute-force scan -- one CTA per query,
-// 12 N bytes streamed, mostly from L2 -- is microseconds per query and needs no tree.
-// Ties (measure zero) resolve to the lowest index.  Distances in the x0 + (x1 + x2) order.
-__global__ void __launch_bounds__(256) nearest_point_kernel(const float *__restrict__ points,
-                                                            uint32_t num_points,
-                                                            const float *__restrict__ queries,
-                                                            uint32_t *__restrict__ out) {
-    const float qx = queries[3 * (uint64_t)blockIdx.x], qy = queries[3 * (uint64_t)blockIdx.x + 1],
-                qz = queries[3 * (uint64_t)blockIdx.x + 2];
-    float best = __int_as_float(0x7f800000);
-    uint32_t best_i = kNone;
-    for (uint32_t i = threadIdx.x; i < num_points; i += blockDim.x) {
-        float dx = points[3 * (uint64_t)i] - qx, dy = points[3 * (uint64_t)i + 1] - qy,
-              dz = points[3 * (uint64_t)i + 2] - qz;
-        float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
-        if (d2 < best) { // strict: the lowest index among this thread's equals stays
-            best = d2;
-            best_i = i;
+// Nearest point of each query = the Voronoi cell that contains it = the cell a ray from that origin starts
+// in (what scene.py:224-234 gets from radfoam.nn over the AABB tree, aabb_tree.cu:343-415, after a
+// torch.unique over all ray origins).  Ray origins are camera positions: one per frame, a few hundred per
+// training batch.  So the exact brute force is the cheap thing here, if it is tiled: U queries x N points
+// distance evaluations, 12 N bytes of traffic in total (not per query), no tree to build or keep current
+// while the points move every step.
+//   nearest_points_kernel: a CTA streams its share of the points through shared memory in tiles; its 256
+//     threads are Uc query lanes x S sub-slices (Uc = min(256, next power of two of U)), so every shared-
+//     memory read is a broadcast (or conflict-free) and U = 1 keeps all lanes busy as well; per thread a
+//     running (distance, index) minimum, merged by one 64-bit atomicMin on the packed key -- distance bits
+//     (non-negative floats order like integers) above the index, i.e. exactly "smallest distance, lowest
+//     index among equals".  Distances in the x0 + (x1 + x2) fma order.  A query without any comparable
+//     distance (NaN) keeps the all-ones key, whose low word is kNone.
+//   U comes from the host or, for the fused start-point path below, from device memory (no host sync).
+constexpr int kNNTile = 1024;
+
+__global__ void __launch_bounds__(256) nearest_points_kernel(const float *__restrict__ points, uint32_t num_points,
+                                                             const float *__restrict__ queries,
+                                                             uint32_t num_queries_host,
+                                                             const uint32_t *__restrict__ num_queries_dev,
+                                                             unsigned long long *__restrict__ best) {
+    __shared__ float4 tile[kNNTile];
+    const uint32_t U = num_queries_dev ? *num_queries_dev : num_queries_host;
+    if (U == 0)
+        return;
+    uint32_t Uc = 1;
+    while (Uc < U && Uc < 256u)
+        Uc <<= 1;
+    const uint32_t S = 256u / Uc, ql = threadIdx.x % Uc, sub = threadIdx.x / Uc;
+    for (uint32_t q0 = 0; q0 < U; q0 += Uc) {
+        const uint32_t q = q0 + ql;
+        const bool live = q < U;
+        float qx = 0.0f, qy = 0.0f, qz = 0.0f;
+        if (live) {
+            qx = queries[3 * (uint64_t)q];
+            qy = queries[3 * (uint64_t)q + 1];
+            qz = queries[3 * (uint64_t)q + 2];
         }
-    }
-    // (distance, index) lexicographic min over the CTA
-    __shared__ float s_d[8];
-    __shared__ uint32_t s_i[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float od = __shfl_down_sync(0xffffffffu, best, o);
-        uint32_t oi = __shfl_down_sync(0xffffffffu, best_i, o);
-        if (od < best || (od == best && oi < best_i)) {
-            best = od;
-            best_i = oi;
+        float best_d = __int_as_float(0x7f800000);
+        uint32_t best_i = kNone;
+        for (uint64_t t0 = (uint64_t)blockIdx.x * kNNTile; t0 < num_points; t0 += (uint64_t)gridDim.x * kNNTile) {
+            __syncthreads();
+            const uint32_t cnt = (uint32_t)(num_points - t0 < (uint64_t)kNNTile ? num_points - t0 : kNNTile);
+            for (uint32_t i = threadIdx.x; i < cnt; i += 256u)
+                tile[i] = make_float4(points[3 * (t0 + i)], points[3 * (t0 + i) + 1], points[3 * (t0 + i) + 2], 0.0f);
+            __syncthreads();
+            if (live)
+                for (uint32_t i = sub; i < cnt; i += S) {
+                    const float4 pt = tile[i];
+                    const float dx = pt.x - qx, dy = pt.y - qy, dz = pt.z - qz;
+                    const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+                    if (d2 < best_d) { // strict: the lowest index among this thread's equals stays
+                        best_d = d2;
+                        best_i = (uint32_t)t0 + i;
+                    }
+                }
         }
+        if (live && best_i != kNone)
+            atomicMin(best + q, ((unsigned long long)__float_as_uint(best_d) << 32) | best_i);
     }
-    if ((threadIdx.x & 31) == 0) {
-        s_d[threadIdx.x >> 5] = best;
-        s_i[threadIdx.x >> 5] = best_i;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
-            if (s_d[w] < best || (s_d[w] == best && s_i[w] < best_i)) {
-                best = s_d[w];
-                best_i = s_i[w];
+}
+
+__global__ void nearest_points_finish_kernel(const unsigned long long *__restrict__ best, uint32_t num_queries,
+                                             uint32_t *__restrict__ indices) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < num_queries)
+        indices[q] = (uint32_t)best[q]; // all-ones (never updated) -> kNone
+}
+
+// Start cell of every ray without a sort and without a host round trip (mirror of get_starting_point,
+// scene.py:224-234): (1) the distinct ray origins are found with an open-addressing hash set keyed on the
+// origin's bits; a table entry is just the index (+1) of the ray that claimed it, whose origin later arrivals
+// compare with, so nothing has to be published before it is read.  Entries are read before they are CASed, so
+// the 2 M rays of one camera cost a handful of atomics, not 2 M.  The claimer appends its origin to a dense
+// query list.  (2) nearest_points_kernel over that list, its length read from device memory.  (3) every ray
+// looks its start cell up through its table slot.  The table has >= 2 R entries, so it cannot fill up.
+__global__ void origin_slots_kernel(const float *__restrict__ rays, uint32_t num_rays, uint32_t *table,
+                                    uint32_t mask, uint32_t *__restrict__ slot_of_ray,
+                                    uint32_t *__restrict__ query_of_slot, float *__restrict__ queries,
+                                    uint32_t *num_queries) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_rays)
+        return;
+    const uint32_t *bits = reinterpret_cast<const uint32_t *>(rays);
+    const uint32_t ox = bits[6 * (uint64_t)r], oy = bits[6 * (uint64_t)r + 1], oz = bits[6 * (uint64_t)r + 2];
+    uint32_t h = (ox * 0x9E3779B1u) ^ (oy * 0x85EBCA77u) ^ (oz * 0xC2B2AE3Du);
+    h ^= h >> 15;
+    for (h &= mask;; h = (h + 1u) & mask) {
+        uint32_t owner = *reinterpret_cast<volatile uint32_t *>(table + h);
+        if (owner == 0u) {
+            owner = atomicCAS(table + h, 0u, r + 1u);
+            if (owner == 0u) { // claimed: this ray's origin becomes a query
+                const uint32_t qn = atomicAdd(num_queries, 1u);
+                query_of_slot[h] = qn;
+                queries[3 * (uint64_t)qn] = __uint_as_float(ox);
+                queries[3 * (uint64_t)qn + 1] = __uint_as_float(oy);
+                queries[3 * (uint64_t)qn + 2] = __uint_as_float(oz);
+                slot_of_ray[r] = h;
+                return;
             }
-        out[blockIdx.x] = best_i;
+        }
+        const uint64_t o = (uint64_t)(owner - 1u) * 6;
+        if (bits[o] == ox && bits[o + 1] == oy && bits[o + 2] == oz) {
+            slot_of_ray[r] = h;
+            return;
+        }
     }
+}
+
+__global__ void start_points_scatter_kernel(const uint32_t *__restrict__ slot_of_ray, uint32_t num_rays,
+                                            const uint32_t *__restrict__ query_of_slot,
+                                            const unsigned long long *__restrict__ best,
+                                            uint32_t *__restrict__ start) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < num_rays)
+        start[r] = (uint32_t)best[query_of_slot[slot_of_ray[r]]];
 }
 
 // ------------------------------------------------------------------ farthest neighbour

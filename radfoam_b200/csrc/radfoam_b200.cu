@@ -120,6 +120,9 @@ struct rfb_pipeline {
     // multi-GPU reduction); nullptr = the pipeline's own `acc`
     float *acc_external = nullptr;
     uint64_t acc_external_floats = 0;
+    // parameter-form scene (rfb_bind_scene_params): attributes are derived from these inside the re-layout kernel
+    rfb_scene_params params = {nullptr, nullptr, nullptr, 1.0f};
+    bool params_bound = false;
     // walk tape (forward records, backward replays; see foam_kernels.cuh)
     DeviceBuffer tape_pool, tape_table, tape_per_ray, tape_ctrl;
     uint32_t tape_capacity = 0;      // chunks
@@ -185,14 +188,28 @@ int scene_checksum(rfb_pipeline *p, uint32_t n, const float *points, const void 
     return 0;
 }
 
+// Is `stream` being captured into a CUDA graph?  Then nothing host-visible may be attached to it: no events
+// that the host (or another stream) later queries, no read-back.  A captured step replays with the buffers it
+// was captured with; the library's bookkeeping (tape growth, cross-stream ordering) resumes outside the graph.
+bool capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 // make `stream` wait for work recorded in `ev` on `producer` (no-op on the same stream)
 int wait_for(cudaEvent_t ev, cudaStream_t producer, cudaStream_t stream) {
-    if (ev && producer != stream)
+    if (ev && producer != stream && !capturing(stream))
         RFB_CUDA(cudaStreamWaitEvent(stream, ev, 0));
     return 0;
 }
 
 int mark(cudaEvent_t &ev, cudaStream_t &producer, cudaStream_t stream) {
+    if (capturing(stream))
+        return 0;
     if (!ev)
         RFB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     RFB_CUDA(cudaEventRecord(ev, stream));
@@ -234,7 +251,18 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
     RFB_CUDA(p->cells.ensure((size_t)n * sizeof(float4)));
     RFB_CUDA(p->sh_rows.ensure((size_t)n * SR * sizeof(float)));
-    if (n) {
+    if (n && p->params_bound) {
+        int grid = grid_for((uint64_t)n * 32, 256);
+        if (p->attr_dtype == RFB_FLOAT16)
+            RFB_LAUNCH((build_cells_params_kernel<__half>), grid, 256, 0, stream, points, p->params.att_dc,
+                       p->params.att_sh, p->params.density, p->params.activation_scale, n, A, SR,
+                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+        else
+            RFB_LAUNCH((build_cells_params_kernel<float>), grid, 256, 0, stream, points, p->params.att_dc,
+                       p->params.att_sh, p->params.density, p->params.activation_scale, n, A, SR,
+                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+        RFB_LAUNCHED();
+    } else if (n) {
         int grid = grid_for((uint64_t)n * 32, 256);
         if (p->attr_dtype == RFB_FLOAT16)
             RFB_LAUNCH((build_cells_kernel<__half>), grid, 256, 0, stream, points,
@@ -282,7 +310,7 @@ void ray_grid(uint32_t num_rays, uint32_t image_width, uint32_t &blocks, uint32_
 }
 
 int profile_mark(rfb_pipeline *p, int which, cudaStream_t stream) {
-    if (!p->profiling)
+    if (!p->profiling || capturing(stream))
         return 0;
     if (!p->ev[which])
         RFB_CUDA(cudaEventCreate(&p->ev[which]));
@@ -575,17 +603,93 @@ int rfb_prefetch_adjacent_diff(const float *points, uint32_t num_points, uint32_
     return 0;
 }
 
+namespace {
+// Stream-ordered scratch from the device's default memory pool; freed blocks stay in the pool (the default
+// release threshold of 0 hands them back to the driver at the next synchronisation: ~2 ms per call measured).
+int stream_scratch(void **ptr, size_t bytes, cudaStream_t stream) {
+    static std::once_flag pool_once;
+    std::call_once(pool_once, [] {
+        int dev = 0;
+        cudaMemPool_t pool = nullptr;
+        uint64_t keep = ~0ull;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
+    });
+    if (cudaMallocAsync(ptr, bytes, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return fail("out of device memory for " + std::to_string(bytes) + " bytes of scratch");
+    }
+    return 0;
+}
+} // namespace
+
 int rfb_nearest_point(const float *points, uint32_t num_points, const float *queries,
-                      uint32_t num_queries, uint32_t *indices, void *stream) {
+                      uint32_t num_queries, uint32_t *indices, void *stream_) {
     if (num_queries == 0)
         return 0;
     if (!points || !queries || !indices)
         return fail("rfb_nearest_point: NULL argument");
     if (num_points == 0)
         return fail("rfb_nearest_point: empty point set");
-    RFB_LAUNCH((rfb::nearest_point_kernel), num_queries, 256, 0, (cudaStream_t)stream, points, num_points,
-               queries, indices);
-    RFB_LAUNCHED();
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *best = nullptr;
+    if (int rc = stream_scratch(reinterpret_cast<void **>(&best), sizeof(unsigned long long) * num_queries, stream))
+        return rc;
+    cudaMemsetAsync(best, 0xFF, sizeof(unsigned long long) * num_queries, stream);
+    const int grid = grid_for((uint64_t)num_points, rfb::kNNTile, 148 * 4);
+    RFB_LAUNCH((rfb::nearest_points_kernel), grid, 256, 0, stream, points, num_points, queries, num_queries,
+               (const uint32_t *)nullptr, best);
+    RFB_LAUNCH((rfb::nearest_points_finish_kernel), (num_queries + 255) / 256, 256, 0, stream, best, num_queries,
+               indices);
+    g_launches += 2;
+    const cudaError_t launched = cudaGetLastError();
+    cudaFreeAsync(best, stream); // stream-ordered: after the kernels above, also on the error path
+    RFB_CUDA(launched);
+    return 0;
+}
+
+int rfb_start_points(const float *points, uint32_t num_points, const float *rays, uint32_t num_rays,
+                     uint32_t *start_point_index, void *stream_) {
+    if (num_rays == 0)
+        return 0;
+    if (!points || !rays || !start_point_index)
+        return fail("rfb_start_points: NULL argument");
+    if (num_points == 0)
+        return fail("rfb_start_points: empty point set");
+    if (num_rays > 0x7FFFFFF0u)
+        return fail("rfb_start_points: too many rays");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    uint32_t table_size = 1024;
+    while (table_size < 2u * num_rays)
+        table_size <<= 1;
+    // one scratch block: [best: R x u64][queries: R x 3 f32][table: T u32][query_of_slot: T u32]
+    //                    [slot_of_ray: R u32][count: 4 u32]
+    const size_t best_b = sizeof(unsigned long long) * (size_t)num_rays, query_b = 12 * (size_t)num_rays,
+                 table_b = 4 * (size_t)table_size, slot_b = 4 * (size_t)num_rays;
+    char *base = nullptr;
+    if (int rc = stream_scratch(reinterpret_cast<void **>(&base), best_b + query_b + 2 * table_b + slot_b + 16, stream))
+        return rc;
+    auto *best = reinterpret_cast<unsigned long long *>(base);
+    auto *queries = reinterpret_cast<float *>(base + best_b);
+    auto *table = reinterpret_cast<uint32_t *>(base + best_b + query_b);
+    auto *query_of_slot = table + table_size;
+    auto *slot_of_ray = query_of_slot + table_size;
+    auto *count = slot_of_ray + num_rays;
+    cudaMemsetAsync(best, 0xFF, best_b, stream);
+    cudaMemsetAsync(table, 0, table_b, stream);
+    cudaMemsetAsync(count, 0, 16, stream);
+    const uint32_t ray_grid = (num_rays + 255) / 256;
+    RFB_LAUNCH((rfb::origin_slots_kernel), ray_grid, 256, 0, stream, rays, num_rays, table, table_size - 1,
+               slot_of_ray, query_of_slot, queries, count);
+    RFB_LAUNCH((rfb::nearest_points_kernel), grid_for((uint64_t)num_points, rfb::kNNTile, 148 * 4), 256, 0, stream,
+               points, num_points, (const float *)queries, 0u, (const uint32_t *)count, best);
+    RFB_LAUNCH((rfb::start_points_scatter_kernel), ray_grid, 256, 0, stream, (const uint32_t *)slot_of_ray, num_rays,
+               (const uint32_t *)query_of_slot, (const unsigned long long *)best, start_point_index);
+    g_launches += 3;
+    const cudaError_t launched = cudaGetLastError();
+    cudaFreeAsync(base, stream);
+    RFB_CUDA(launched);
     return 0;
 }
 
@@ -617,6 +721,8 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
         return fail("rfb_trace_forward: pipeline is NULL");
     if (num_rays == 0)
         return 0;
+    if (p->params_bound)
+        attributes = p->params.density; // identity for the mirror cache; the values come from the bound parameters
     if (!points || !attributes || !point_adjacency || !point_adjacency_offsets || !rays ||
         !start_point_index || !ray_rgba)
         return fail("rfb_trace_forward: NULL argument");
@@ -663,10 +769,12 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     if (int rc = profile_mark(p, 1, stream))
         return rc;
     if (record) {
-        RFB_CUDA(cudaMemcpyAsync(p->tape_readback, p->tape_ctrl.ptr, 2 * sizeof(uint32_t),
-                                 cudaMemcpyDeviceToHost, stream));
-        RFB_CUDA(cudaEventRecord(p->tape_readback_done, stream));
-        p->tape_readback_pending = true;
+        if (!capturing(stream)) {
+            RFB_CUDA(cudaMemcpyAsync(p->tape_readback, p->tape_ctrl.ptr, 2 * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, stream));
+            RFB_CUDA(cudaEventRecord(p->tape_readback_done, stream));
+            p->tape_readback_pending = true;
+        }
         p->tape_key.rays = rays;
         p->tape_key.start = start_point_index;
         p->tape_key.num_rays = num_rays;
@@ -710,6 +818,8 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
     p->acc_points = num_points;
     if (num_rays == 0)
         return 0;
+    if (p->params_bound)
+        attributes = p->params.density;
     if (!points || !attributes || !point_adjacency || !point_adjacency_offsets || !rays ||
         !start_point_index || !ray_rgba || !ray_rgba_grad)
         return fail("rfb_trace_backward: NULL argument");
@@ -861,6 +971,51 @@ int rfb_trace_backward_finalize(rfb_pipeline *p, uint32_t num_points, float *poi
     return 0;
 }
 
+int rfb_bind_scene_params(rfb_pipeline *p, const rfb_scene_params *params) {
+    if (!p)
+        return fail("rfb_bind_scene_params: pipeline is NULL");
+    p->key_valid = false;
+    if (!params) {
+        p->params_bound = false;
+        return 0;
+    }
+    if (!params->att_dc || !params->density || (p->sh_degree > 0 && !params->att_sh))
+        return fail("rfb_bind_scene_params: NULL parameter array");
+    p->params = *params;
+    p->params_bound = true;
+    return 0;
+}
+
+int rfb_trace_backward_finalize_params(rfb_pipeline *p, uint32_t num_points, float *points_grad,
+                                       float *att_dc_grad, float *att_sh_grad, float *density_grad,
+                                       uint32_t flags, void *stream_) {
+    if (!p)
+        return fail("rfb_trace_backward_finalize_params: pipeline is NULL");
+    if (!p->params_bound)
+        return fail("rfb_trace_backward_finalize_params: no parameter-form scene is bound");
+    if (num_points == 0)
+        return 0;
+    if (!points_grad || !att_dc_grad || !density_grad || (p->sh_degree > 0 && !att_sh_grad))
+        return fail("rfb_trace_backward_finalize_params: NULL argument");
+    if (num_points != p->acc_points)
+        return fail("rfb_trace_backward_finalize_params: no accumulated gradients for this point count");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
+    int grid = grid_for((uint64_t)num_points * 32, 256);
+    int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
+    const float *acc_ptr = p->acc_external ? p->acc_external : reinterpret_cast<const float *>(p->acc.ptr);
+    if (p->attr_dtype == RFB_FLOAT16)
+        RFB_LAUNCH((finalize_params_kernel<__half>), grid, 256, 0, stream, acc_ptr, p->params.density,
+                   p->params.activation_scale, num_points, A, SR, points_grad, att_dc_grad, att_sh_grad,
+                   density_grad, scrub);
+    else
+        RFB_LAUNCH((finalize_params_kernel<float>), grid, 256, 0, stream, acc_ptr, p->params.density,
+                   p->params.activation_scale, num_points, A, SR, points_grad, att_dc_grad, att_sh_grad,
+                   density_grad, scrub);
+    RFB_LAUNCHED();
+    return 0;
+}
+
 int rfb_trace_backward(rfb_pipeline *p, const rfb_trace_settings *settings, uint32_t num_points,
                        const float *points, const void *attributes, uint32_t point_adjacency_size,
                        const uint32_t *point_adjacency, const uint32_t *point_adjacency_offsets,
@@ -871,6 +1026,9 @@ int rfb_trace_backward(rfb_pipeline *p, const rfb_trace_settings *settings, uint
                        float *ray_grad, float *points_grad, void *attribute_grad, void *point_error,
                        const rfb_launch_opts *opts, void *stream) {
     (void)ray_grad; // never written, like the reference kernel
+    if (p && p->params_bound)
+        return fail("rfb_trace_backward: a parameter-form scene is bound; use rfb_trace_backward_accumulate + "
+                    "rfb_trace_backward_finalize_params");
     if (int rc = rfb_trace_backward_accumulate(
             p, settings, num_points, points, attributes, point_adjacency_size, point_adjacency,
             point_adjacency_offsets, num_rays, rays, start_point_index, num_depth_quantiles,

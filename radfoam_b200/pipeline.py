@@ -65,6 +65,7 @@ class Pipeline:
         # (inside Function.forward grad mode is always off; None = not called through such an op)
         self.autograd_recording = None
         self._external_acc = None  # keeps a caller-provided accumulator alive (set_grad_accumulator)
+        self._params = None        # bound parameter-form scene (bind_scene_params)
         # unordered ray batches ([R, 6], the reference's training batches: train.py:61) are traced
         # in a coherent order -- sorted by (start cell, direction) -- and the per-ray outputs are
         # scattered back; results are unchanged, neighbouring lanes share cells again
@@ -125,16 +126,22 @@ class Pipeline:
         if points.device.type != "cuda":
             raise RuntimeError("points must be on CUDA device")
         num_points = points.numel() // 3
-        if attributes.size(-1) != self._attr_dim:
-            raise RuntimeError(f"attributes had dimension {attributes.size(-1)} along axis -1, "
-                               f"expected {self._attr_dim}")
-        if attributes.numel() // self._attr_dim != num_points:
-            raise RuntimeError("attributes must have the same number of rows as points")
-        if attributes.dtype != self._dtype:
-            raise RuntimeError(f"attributes had dtype {_dtype_name(attributes.dtype)}, "
-                               f"expected {_dtype_name(self._dtype)}")
-        if attributes.device.type != "cuda":
-            raise RuntimeError("attributes must be on CUDA device")
+        if attributes is None:
+            if self._params is None:
+                raise RuntimeError("attributes is None but no parameter-form scene is bound (bind_scene_params)")
+        else:
+            if self._params is not None:
+                raise RuntimeError("a parameter-form scene is bound: pass attributes=None, or unbind it")
+            if attributes.size(-1) != self._attr_dim:
+                raise RuntimeError(f"attributes had dimension {attributes.size(-1)} along axis -1, "
+                                   f"expected {self._attr_dim}")
+            if attributes.numel() // self._attr_dim != num_points:
+                raise RuntimeError("attributes must have the same number of rows as points")
+            if attributes.dtype != self._dtype:
+                raise RuntimeError(f"attributes had dtype {_dtype_name(attributes.dtype)}, "
+                                   f"expected {_dtype_name(self._dtype)}")
+            if attributes.device.type != "cuda":
+                raise RuntimeError("attributes must be on CUDA device")
         if point_adjacency_offsets.dtype != torch.uint32:
             raise RuntimeError("point_adjacency_offsets must have uint32 dtype")
         if point_adjacency_offsets.device.type != "cuda":
@@ -209,10 +216,12 @@ class Pipeline:
         same = all(r() is t and v == t._version for (r, v), t in zip(refs[:2], (rays_c, start_c)))
         return _lib.FLAG_USE_TAPE if same else 0
 
-    def _backward_expected(self, points, attributes) -> bool:
+    def _backward_expected(self, trainable) -> bool:
         """Will a backward over this forward follow?  (Only then is the walk tape worth recording.)
+        ``trainable`` = (points, attributes) or (points, att_dc, att_sh, density).
         nn.Parameters keep requires_grad under torch.no_grad(), so requires_grad alone is not enough."""
-        if not (points.requires_grad or attributes.requires_grad):
+        points, rest = trainable[0], trainable[1:]
+        if not any(t.requires_grad for t in trainable):
             return False
         if self.autograd_recording is not None:  # told by radfoam_b200's autograd ops
             return bool(self.autograd_recording)
@@ -223,9 +232,9 @@ class Pipeline:
         # off.  A non-leaf input that requires grad only exists while a graph is being recorded.  With leaves
         # only, the reference's eval path gives points (a Parameter) with attributes built under no_grad
         # (scene.py:202-217: requires_grad False); both being trainable leaves means a hand-made training step.
-        if any(t.requires_grad and t.grad_fn is not None for t in (points, attributes)):
+        if any(t.requires_grad and t.grad_fn is not None for t in trainable):
             return True
-        return points.requires_grad and attributes.requires_grad
+        return points.requires_grad and any(t.requires_grad for t in rest)
 
     def _settings(self, weight_threshold, max_intersections):
         s = _lib.TraceSettings(0.001, 1024)  # default_trace_settings(), pipeline.h:15-20
@@ -253,13 +262,10 @@ class Pipeline:
     def trace_forward(self, points, attributes, point_adjacency, point_adjacency_offsets, rays,
                       start_point, depth_quantiles=None, weight_threshold=None,
                       max_intersections=None, return_contribution=False):
-        points_c = points.contiguous()
-        attributes_c = attributes.contiguous()
-        adj_c = point_adjacency.contiguous()
-        off_c = point_adjacency_offsets.contiguous()
+        (points_c, attributes_c, adj_c, off_c), scene_key = self._scene_tensors(
+            points, attributes, point_adjacency, point_adjacency_offsets)
         rays_c = rays.contiguous()
         start_c = start_point.contiguous()
-        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
 
         return_depth = depth_quantiles is not None
         num_points = points_c.size(0)
@@ -300,9 +306,9 @@ class Pipeline:
             depth = torch.empty(batch + [num_q], dtype=torch.float32, device=dev)
             depth_indices = torch.empty(batch + [num_q], dtype=torch.uint32, device=dev)
 
-        record = self.record_tape and self.cache_scene and self._backward_expected(points, attributes)
-        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c,
-                          _lib.FLAG_RECORD_TAPE if record else 0)
+        trainable = (points, attributes) if attributes is not None else (points,) + self._params[1]
+        record = self.record_tape and self.cache_scene and self._backward_expected(trainable)
+        opts = self._opts(scene_key, rays_c, _lib.FLAG_RECORD_TAPE if record else 0)
         self._tape_refs = ([(weakref.ref(t), t._version) for t in (rays_c, start_c)]
                            + [opts.scene_version] if record else None)
         with torch.cuda.device(dev):
@@ -344,13 +350,10 @@ class Pipeline:
                        start_point, rgb_out, grad_in, depth_quantiles, depth_indices,
                        depth_grad_in, ray_error):
         """Shared validation of trace_backward (pipeline_bindings.cpp:267-439)."""
-        points_c = points.contiguous()
-        attributes_c = attributes.contiguous()
-        adj_c = point_adjacency.contiguous()
-        off_c = point_adjacency_offsets.contiguous()
+        (points_c, attributes_c, adj_c, off_c), scene_key = self._scene_tensors(
+            points, attributes, point_adjacency, point_adjacency_offsets)
         rays_c = rays.contiguous()
         start_c = start_point.contiguous()
-        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
         num_rays = rays_c.numel() // 6
         self._validate_rays(rays_c, start_c, num_rays)
 
@@ -413,6 +416,7 @@ class Pipeline:
                 raise RuntimeError("ray_error must be on CUDA device")
             if err_c.numel() != num_rays:
                 raise RuntimeError("ray_error must have the same batch size as rays")
+        self._scene_key = scene_key
         return (points_c, attributes_c, adj_c, off_c, rays_c, start_c, rgb_c, grad_c, dq_c, di_c,
                 dg_c, err_c, num_rays, num_q)
 
@@ -435,15 +439,16 @@ class Pipeline:
         dev = rays_c.device
         settings = self._settings(weight_threshold, max_intersections)
         # fully overwritten by the kernels' epilogue: no zero-fill pass needed
-        attr_grad = torch.empty((attributes_c.size(0), self._attr_dim), dtype=self._dtype, device=dev)
+        if attributes_c is None:
+            raise RuntimeError("a parameter-form scene is bound: use trace_backward_params")
+        attr_grad = torch.empty((num_points, self._attr_dim), dtype=self._dtype, device=dev)
         points_grad = torch.empty((num_points, 3), dtype=torch.float32, device=dev)
         ray_grad = torch.empty_like(rays_c)  # never written, like the reference
         point_error = None
         if err_c is not None:
             point_error = torch.zeros((num_points, 1), dtype=self._dtype, device=dev)
 
-        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c,
-                          _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0)
+        opts = self._opts(self._scene_key, rays_c, _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0)
         opts.flags |= self._tape_flag(rays_c, start_c, opts.scene_version)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -480,7 +485,7 @@ class Pipeline:
         point_error = None
         if err_c is not None:
             point_error = torch.zeros((num_points, 1), dtype=self._dtype, device=dev)
-        opts = self._opts((points_c, attributes_c, adj_c, off_c), rays_c)
+        opts = self._opts(self._scene_key, rays_c)
         opts.flags |= self._tape_flag(rays_c, start_c, opts.scene_version)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -500,6 +505,71 @@ class Pipeline:
         if n == 0:
             return torch.empty((0, row), dtype=torch.float32, device=device)
         return _wrap_device_memory(ptr.value, (n, row), device)
+
+    # ---- parameter-form scene: get_trace_data (scene.py:202-217) fused into the re-layout / finalize kernels
+    def bind_scene_params(self, att_dc, att_sh, density, activation_scale=1.0) -> None:
+        """Trace the scene straight from the model's parameters: ``attributes = cat(att_dc, att_sh,
+        activation_scale * softplus(density, beta=10)).to(attr_dtype)`` is evaluated inside the re-layout
+        kernel instead of by torch ops.  While bound, pass ``attributes=None`` to the trace calls and use
+        ``trace_backward_params``.  ``bind_scene_params(None, None, None)`` unbinds."""
+        if att_dc is None:
+            self._params = None
+            _lib.check(self._lib.rfb_bind_scene_params(self._handle, None))
+            return
+        n = density.numel()
+        if self._sh_degree == 0 and att_sh is None:
+            att_sh = torch.empty((n, 0), dtype=torch.float32, device=density.device)
+        for name, t, cols in (("att_dc", att_dc, 3), ("att_sh", att_sh, self._attr_dim - 4), ("density", density, 1)):
+            if t.dtype != torch.float32:
+                raise RuntimeError(f"{name} had dtype {_dtype_name(t.dtype)}, expected float32 (model parameters)")
+            if t.device.type != "cuda":
+                raise RuntimeError(f"{name} must be on CUDA device")
+            if t.numel() != n * cols:
+                raise RuntimeError(f"{name} must have {cols} columns and the same number of rows as density")
+        if not all(t.is_contiguous() for t in (att_dc, att_sh, density)):
+            raise RuntimeError("att_dc, att_sh and density must be contiguous (they are read in place)")
+        tensors = tuple(t.detach() for t in (att_dc, att_sh, density))  # share storage and version counter
+        self._params = (tensors, (att_dc, att_sh, density), float(activation_scale))
+        sp = _lib.SceneParams(tensors[0].data_ptr(), tensors[1].data_ptr() if tensors[1].numel() else None,
+                              tensors[2].data_ptr(), float(activation_scale))
+        _lib.check(self._lib.rfb_bind_scene_params(self._handle, ctypes.byref(sp)))
+
+    def trace_backward_params(self, points, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out,
+                              grad_in, depth_quantiles=None, depth_indices=None, depth_grad_in=None, ray_error=None,
+                              weight_threshold=None, max_intersections=None, scrub_nonfinite=True):
+        """Backward of a bound parameter-form scene: gradients of points, att_dc, att_sh and the raw density."""
+        if self._params is None:
+            raise RuntimeError("no parameter-form scene is bound (bind_scene_params)")
+        _, point_error = self.trace_backward_accumulate(
+            points, None, point_adjacency, point_adjacency_offsets, rays, start_point, rgb_out, grad_in,
+            depth_quantiles, depth_indices, depth_grad_in, ray_error, weight_threshold, max_intersections)
+        n, dev = points.shape[0], rays.device
+        out = {"points_grad": torch.empty((n, 3), dtype=torch.float32, device=dev),
+               "att_dc_grad": torch.empty((n, 3), dtype=torch.float32, device=dev),
+               "att_sh_grad": torch.empty((n, self._attr_dim - 4), dtype=torch.float32, device=dev),
+               "density_grad": torch.empty((n, 1), dtype=torch.float32, device=dev)}
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._lib.rfb_trace_backward_finalize_params(
+                self._handle, n, _ptr(out["points_grad"]), _ptr(out["att_dc_grad"]),
+                _ptr(out["att_sh_grad"]) if out["att_sh_grad"].numel() else None, _ptr(out["density_grad"]),
+                _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, stream))
+        if point_error is not None:
+            out["point_error"] = point_error
+        return out
+
+    def _scene_tensors(self, points, attributes, point_adjacency, point_adjacency_offsets):
+        """Validated, contiguous ``(points, attributes, adjacency, offsets)`` + the tensors whose identity and
+        version key the mirror cache.  With a bound parameter-form scene ``attributes`` is None and the three
+        parameter tensors take its place in the key."""
+        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
+        scene = (points.contiguous(), None if attributes is None else attributes.contiguous(),
+                 point_adjacency.contiguous(), point_adjacency_offsets.contiguous())
+        if self._params is None:
+            return scene, scene
+        if self._params[0][2].numel() != points.numel() // 3:
+            raise RuntimeError("the bound parameters must have the same number of rows as points")
+        return scene, (scene[0],) + self._params[0] + scene[2:]
 
     def set_grad_accumulator(self, acc) -> None:
         """Scatter the backward into caller-provided memory (an ``[N, grad_row_floats]`` float32 CUDA tensor the
@@ -537,12 +607,9 @@ class Pipeline:
     def trace_benchmark(self, points, attributes, point_adjacency, point_adjacency_offsets,
                         adjacent_diff, camera, start_point, output_rgba, weight_threshold=None,
                         max_intersections=None):
-        points_c = points.contiguous()
-        attributes_c = attributes.contiguous()
-        adj_c = point_adjacency.contiguous()
-        off_c = point_adjacency_offsets.contiguous()
+        (points_c, attributes_c, adj_c, off_c), scene_key = self._scene_tensors(
+            points, attributes, point_adjacency, point_adjacency_offsets)
         diff_c = adjacent_diff.contiguous()
-        self._validate_scene(points, attributes, point_adjacency, point_adjacency_offsets)
         num_points = points_c.size(0)
 
         cam = _lib.Camera()
@@ -581,7 +648,7 @@ class Pipeline:
 
         settings = self._settings(weight_threshold, max_intersections)
         dev = points_c.device
-        opts = self._opts((points_c, attributes_c, adj_c, off_c), None)
+        opts = self._opts(scene_key, None)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(self._lib.rfb_trace_benchmark(
@@ -622,7 +689,7 @@ def _wrap_device_memory(ptr: int, shape, device) -> torch.Tensor:
 
 
 def nearest_point(points, queries):
-    """Entry cells: index of the nearest point of each query, ``uint32[M]`` (exact brute force on
+    """Entry cells: index of the nearest point of each query, ``uint32[M]`` (exact, tiled brute force on
     the GPU; stands in for ``radfoam.nn(points, aabb_tree, queries)`` where the tracer needs it,
     radfoam_model/scene.py:224-234, benchmark.py:88-89)."""
     pts = points.detach().contiguous()
@@ -639,17 +706,23 @@ def nearest_point(points, queries):
 
 
 def starting_points(rays, points):
-    """Start cell of every ray (mirror of RadFoamScene.get_starting_point, scene.py:224-234):
-    one nearest-point query per distinct ray origin, scattered back to the rays' batch shape."""
-    with torch.no_grad():
-        origins = rays[..., :3].reshape(-1, 3)
-        if origins.size(0) and bool((origins == origins[0]).all()):
-            # one camera (a rendered frame): a single query, broadcast
-            idx = nearest_point(points, origins[:1])
-            return idx.to(torch.int64).expand(origins.size(0)).to(torch.uint32).reshape(rays.shape[:-1])
-        unique, inverse = torch.unique(origins, dim=0, return_inverse=True)
-        idx = nearest_point(points, unique).to(torch.int64)
-        return idx[inverse].to(torch.uint32).reshape(rays.shape[:-1])
+    """Start cell of every ray (mirror of RadFoamScene.get_starting_point, scene.py:224-234): the nearest point
+    of each ray's origin, in the rays' batch shape.  One library call -- device-side de-duplication of the
+    origins (no ``torch.unique`` sort over the rays), one exact lookup per distinct origin, no host sync."""
+    pts = points.detach().contiguous()
+    r = rays.detach()
+    if pts.dtype != torch.float32 or pts.size(-1) != 3:
+        raise RuntimeError("points must be float32 [N, 3]")
+    if r.size(-1) != 6 or r.dtype != torch.float32:
+        raise RuntimeError("rays must be float32 [..., 6]")
+    if pts.device.type != "cuda" or r.device != pts.device:
+        raise RuntimeError("points and rays must be on the same CUDA device")
+    r = r.contiguous()
+    out = torch.empty(r.shape[:-1], dtype=torch.uint32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        stream = torch.cuda.current_stream(pts.device).cuda_stream
+        _lib.check(_lib.load().rfb_start_points(_ptr(pts), pts.size(0), _ptr(r), r.numel() // 6, _ptr(out), stream))
+    return out
 
 
 def farthest_neighbor(points, point_adjacency, point_adjacency_offsets):

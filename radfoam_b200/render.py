@@ -75,3 +75,56 @@ class TraceRays(torch.autograd.Function):
         box.point_error = grads.get("point_error")
         ctx.pipeline = None
         return (None, grads["points_grad"], grads["attr_grad"]) + (None,) * 6
+
+
+class TraceRaysParams(torch.autograd.Function):
+    """The render op taken one step further out: ``RadFoamScene.forward`` = ``get_trace_data`` (a ``cat`` and a
+    softplus, scene.py:202-217) followed by ``TraceRays`` (scene.py:236-261).  Here the model's PARAMETERS go in --
+    ``(pipeline, points, att_dc, att_sh, density, activation_scale, point_adjacency, point_adjacency_offsets, rays,
+    start_point, depth_quantiles, return_contribution)`` -- and their gradients come out; the attribute matrix and
+    its gradient are never materialised (the re-layout and finalize kernels read / write the parameters directly).
+    Same outputs as :class:`TraceRays`."""
+
+    @classmethod
+    def apply(cls, pipeline, *args):
+        before, pipeline.autograd_recording = pipeline.autograd_recording, torch.is_grad_enabled()
+        try:
+            return super().apply(pipeline, *args)
+        finally:
+            pipeline.autograd_recording = before
+
+    @staticmethod
+    def forward(ctx, pipeline, points, att_dc, att_sh, density, activation_scale, point_adjacency,
+                point_adjacency_offsets, rays, start_point, depth_quantiles, return_contribution):
+        pipeline.bind_scene_params(att_dc, att_sh, density, activation_scale)
+        try:
+            out = pipeline.trace_forward(points, None, point_adjacency, point_adjacency_offsets, rays, start_point,
+                                         depth_quantiles=depth_quantiles, return_contribution=return_contribution)
+        finally:
+            pipeline.bind_scene_params(None, None, None)
+        rgba = out["rgba"]
+        saved = [points, att_dc, att_sh, density, point_adjacency, point_adjacency_offsets, rays, start_point, rgba]
+        ctx.with_depth = depth_quantiles is not None
+        if ctx.with_depth:
+            saved += [depth_quantiles, out["depth_indices"]]
+        ctx.save_for_backward(*saved)
+        ctx.pipeline, ctx.activation_scale = pipeline, activation_scale
+        ctx.errbox = box = ErrorBox()
+        return rgba, out.get("depth"), out.get("contribution"), out["num_intersections"], box
+
+    @staticmethod
+    def backward(ctx, grad_rgba, grad_depth, _grad_contribution, _grad_num_intersections, _grad_box):
+        saved = ctx.saved_tensors
+        points, att_dc, att_sh, density, adjacency, offsets, rays, start_point, rgba = saved[:9]
+        quantiles, depth_indices = (saved[9], saved[10]) if ctx.with_depth else (None, None)
+        pipeline, box = ctx.pipeline, ctx.errbox
+        pipeline.bind_scene_params(att_dc, att_sh, density, ctx.activation_scale)
+        try:
+            grads = pipeline.trace_backward_params(points, adjacency, offsets, rays, start_point, rgba, grad_rgba,
+                                                   quantiles, depth_indices, grad_depth, box.ray_error,
+                                                   scrub_nonfinite=True)
+        finally:
+            pipeline.bind_scene_params(None, None, None)
+        box.point_error = grads.get("point_error")
+        ctx.pipeline = None
+        return (None, grads["points_grad"], grads["att_dc_grad"], grads["att_sh_grad"], grads["density_grad"]) + (None,) * 7

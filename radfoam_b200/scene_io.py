@@ -60,6 +60,27 @@ class FoamScene:
         attributes = torch.cat([self.get_primal_attributes(), self.get_primal_density()], dim=-1).to(self.attr_dtype)
         return self.primal_points, attributes, self.point_adjacency, self.point_adjacency_offsets
 
+    # ------------------------------------------------------------------ scene.py:236-261
+    def forward(self, pipeline, rays, start_point=None, depth_quantiles=None, return_contribution=False, fused=True):
+        """``RadFoamScene.forward``: ``(rgba, depth, contribution, num_intersections, errbox)``.  ``fused`` (fp32
+        parameters only) hands the parameters to the kernels instead of building the attribute matrix with torch
+        ops -- same values, same gradients, 3-5 fewer passes over ``[N, 49]`` per step."""
+        from . import pipeline as _p
+        from .render import TraceRays, TraceRaysParams
+
+        points = self.primal_points
+        if start_point is None:
+            start_point = _p.starting_points(rays, points)
+        else:
+            start_point = torch.broadcast_to(start_point, rays.shape[:-1])
+        if fused and self.att_dc.dtype == torch.float32 and self.density.dtype == torch.float32:
+            return TraceRaysParams.apply(pipeline, points, self.att_dc, self.att_sh, self.density,
+                                         self.activation_scale, self.point_adjacency, self.point_adjacency_offsets,
+                                         rays, start_point, depth_quantiles, return_contribution)
+        points, attributes, adjacency, offsets = self.get_trace_data()
+        return TraceRays.apply(pipeline, points, attributes, adjacency, offsets, rays, start_point, depth_quantiles,
+                               return_contribution)
+
     @property
     def num_points(self) -> int:
         return int(self.primal_points.shape[0])

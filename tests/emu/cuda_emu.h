@@ -375,6 +375,16 @@ inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+inline unsigned atomicCAS(unsigned *p, unsigned expected, unsigned desired) {
+    __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expected; // the old value either way
+}
 inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline void rfb_emu_red_add_v4(float *p, float a, float b, float c, float d) {
     emu::counters.red_v4.fetch_add(1, std::memory_order_relaxed);
@@ -457,6 +467,7 @@ inline T __shfl_down_sync(unsigned mask, T value, unsigned delta, int width = 32
 #define cudaMemcpyAsync(d, s, n, kind, st) (std::memcpy((d), (s), (n)), cudaSuccess)
 #define cudaStreamSynchronize(s) (cudaSuccess)
 #define cudaStreamWaitEvent(s, e, f) (cudaSuccess)
+#define cudaStreamIsCapturing(s, st) (*(st) = cudaStreamCaptureStatusNone, cudaSuccess)
 #define cudaMemGetInfo(f, t) (*(f) = (size_t)1 << 40, *(t) = (size_t)1 << 40, cudaSuccess)
 #define cudaGetLastError() (cudaSuccess)
 #define cudaGetErrorString(e) ("emulated CUDA runtime error")

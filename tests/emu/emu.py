@@ -225,6 +225,13 @@ def nearest_point(points, queries):
     return out
 
 
+def start_points(points, rays):
+    pts, r = _c(points, np.float32), _c(rays, np.float32)
+    out = np.zeros(r.shape[:-1], np.uint32)
+    _check(load().rfb_start_points(_p(pts), pts.shape[0], _p(r), r.size // 6, _p(out), None))
+    return out
+
+
 def farthest_neighbor(points, adjacency, offsets):
     pts, adj, off = _c(points, np.float32), _c(adjacency, np.uint32), _c(offsets, np.uint32)
     idx, radius = np.zeros((pts.shape[0],), np.uint32), np.zeros((pts.shape[0],), np.float32)

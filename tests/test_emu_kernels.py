@@ -160,6 +160,50 @@ def test_small_csr_passes_bit_exact(small_scene):
     assert np.array_equal(emu.nearest_point(f.points, queries), d2.argmin(axis=1).astype(np.uint32))
 
 
+@pytest.mark.parametrize("num_queries", [1, 2, 31, 257, 600])
+def test_nearest_point_tiled_layouts(num_queries):
+    """Every CTA layout of the tiled brute force (query lanes x sub-slices; more than 256 queries = several
+    batches), ragged last tile, an exact tie (lowest index wins) and a NaN query (-> UINT32_MAX)."""
+    rng = np.random.default_rng(num_queries)
+    pts = rng.normal(0, 1, size=(2500, 3)).astype(np.float32)
+    pts[1700] = pts[300]                       # duplicate point: the tie goes to index 300
+    q = rng.normal(0, 1.5, size=(num_queries, 3)).astype(np.float32)
+    q[0] = pts[1700]
+    if num_queries > 2:
+        q[2, 1] = np.nan
+    got = emu.nearest_point(pts, q)
+    d = pts[None, :, :] - q[:, None, :]
+    # float32 distances in the kernel's own order: fma(dx,dx, fma(dy,dy, dz*dz)), each fma rounded once
+    d64 = d.astype(np.float64)
+    inner = (d64[..., 1] * d64[..., 1] + (d[..., 2] * d[..., 2]).astype(np.float64)).astype(np.float32)
+    dist = (d64[..., 0] * d64[..., 0] + inner.astype(np.float64)).astype(np.float32)
+    want = np.where(np.isnan(dist).all(axis=1), 0xFFFFFFFF, np.nanargmin(np.where(np.isnan(dist), np.inf, dist), axis=1))
+    assert np.array_equal(got, want.astype(np.uint32))
+    assert got[0] == 300
+
+
+def test_start_points_dedupes_origins_on_the_device():
+    """rfb_start_points == nearest point of every ray's origin, for one camera (a frame), a few cameras
+    (a training batch), per-ray distinct origins, and odd origins (+0 / -0, NaN)."""
+    rng = np.random.default_rng(12)
+    f = common.scene_case(num_points=8000, width=32, height=16, q=2).foam
+    cams = rng.normal(0, 2, size=(7, 3)).astype(np.float32)
+    cams[5] = [0.0, 1.0, -0.0]
+    cams[6] = [-0.0, 1.0, 0.0]                 # same point as cams[5], different bits: two queries, one answer
+    ref = emu.nearest_point(f.points, cams)
+    which = rng.integers(0, 7, size=(5, 211))
+    rays = np.concatenate([cams[which], rng.normal(size=(5, 211, 3)).astype(np.float32)], axis=-1)
+    assert np.array_equal(emu.start_points(f.points, rays), ref[which])
+    frame = np.broadcast_to(np.concatenate([cams[1], [0, 0, 1]]).astype(np.float32), (9, 13, 6)).copy()
+    assert np.all(emu.start_points(f.points, frame) == ref[1])
+    scattered = rng.normal(0, 2, size=(300, 6)).astype(np.float32)      # every origin distinct
+    assert np.array_equal(emu.start_points(f.points, scattered), emu.nearest_point(f.points, scattered[:, :3]))
+    bad = scattered[:4].copy()
+    bad[2, 0] = np.nan
+    got = emu.start_points(f.points, bad)
+    assert got[2] == 0xFFFFFFFF and np.array_equal(got[[0, 1, 3]], emu.nearest_point(f.points, bad[[0, 1, 3], :3]))
+
+
 @pytest.mark.parametrize("tag", ["f16", "f32"])
 @pytest.mark.parametrize("model", ["pinhole", "fisheye"])
 def test_trace_benchmark_against_reference_kernel_frames(tag, model):

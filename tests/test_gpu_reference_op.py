@@ -167,3 +167,90 @@ def test_native_op_leaves_no_reference_cycle(torch_cuda):
         assert ref() is None, "rgba survived: a reference cycle keeps the step's tensors alive until gc runs"
     finally:
         gc.enable()
+
+
+@pytest.mark.parametrize("attr_dtype", ["float32", "float16"])
+def test_parameter_form_scene_equals_torch_glue(torch_cuda, attr_dtype):
+    """get_trace_data's cat + softplus (scene.py:202-217) and the gradient split back through them,
+    fused into the re-layout / finalize kernels (TraceRaysParams), against the same thing done with torch ops
+    around TraceRays -- values and all four parameter gradients."""
+    import radfoam_b200
+    from radfoam_b200 import scene_io
+
+    torch = torch_cuda
+    case = common.scene_case(20000, 160, 96, q=2)
+    dt = torch.float16 if attr_dtype == "float16" else torch.float32
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    results = []
+    for fused in (False, True):
+        scene = scene_io.FoamScene.from_foam(case.foam, device="cuda", activation_scale=1.7)
+        scene.attr_dtype = dt
+        params = [scene.primal_points, scene.att_dc, scene.att_sh, scene.density]
+        for t in params:
+            t.requires_grad_(True)
+        pipe = radfoam_b200.create_pipeline(3, attr_dtype)
+        rays, start = dev(case.rays), dev(case.start)
+        if fused:
+            out = radfoam_b200.TraceRaysParams.apply(pipe, *params, scene.activation_scale, scene.point_adjacency,
+                                                     scene.point_adjacency_offsets, rays, start, dev(case.quantiles),
+                                                     False)
+        else:
+            points, attributes, adjacency, offsets = scene.get_trace_data()
+            out = radfoam_b200.TraceRays.apply(pipe, points, attributes, adjacency, offsets, rays, start,
+                                               dev(case.quantiles), False)
+        rgba, depth, _, nint, _ = out
+        g = dev(case.grad_rgba).to(dt)
+        ((rgba * g).sum().float() + (depth * dev(case.grad_depth)).sum()).backward()
+        results.append(dict(rgba=rgba.detach().float(), depth=depth.detach(), nint=nint,
+                            grads=[t.grad.clone() for t in params]))
+    a, b = results
+    assert torch.equal(a["nint"], b["nint"])
+    assert torch.equal(a["rgba"], b["rgba"]) and torch.equal(a["depth"], b["depth"])  # same attribute values, bit for bit
+    for name, ga, gb in zip(("points", "att_dc", "att_sh", "density"), a["grads"], b["grads"]):
+        assert ga.shape == gb.shape
+        err = float((ga - gb).abs().max() / ga.abs().max().clamp_min(1e-30))
+        assert err <= 1e-5, f"{name}: {err:.3g}"
+
+
+def test_training_step_is_cuda_graph_capturable(torch_cuda):
+    """the path must be graph-capturable.  Re-layout + recording forward + replaying backward +
+    finalize of one step are captured into a CUDA graph (after a warm-up step sized the library's buffers) and
+    replayed on new parameter values; the replay must equal an eager step on the same values."""
+    import radfoam_b200
+
+    torch = torch_cuda
+    case = common.scene_case(20000, 160, 96, q=2)
+    f = case.foam
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    points, attrs = dev(f.points).requires_grad_(True), dev(f.attributes).requires_grad_(True)
+    adj, off, rays, start, dq = dev(f.adjacency), dev(f.offsets), dev(case.rays), dev(case.start), dev(case.quantiles)
+    g, gd = dev(case.grad_rgba), dev(case.grad_depth)
+    pipe = radfoam_b200.create_pipeline(3, "float32")
+
+    def step():
+        pipe.invalidate_cache()  # parameters changed
+        fwd = pipe.trace_forward(points, attrs, adj, off, rays, start, depth_quantiles=dq)
+        bwd = pipe.trace_backward(points, attrs, adj, off, rays, start, fwd["rgba"], g, dq, fwd["depth_indices"], gd,
+                                  scrub_nonfinite=True)
+        return fwd["rgba"], bwd["points_grad"], bwd["attr_grad"]
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):  # sizes the tape pool, the mirrors and the accumulator
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = step()
+    with torch.no_grad():  # "optimizer step": new values in the SAME tensors
+        attrs[:, :48] *= 0.9
+        points += 1e-4
+    graph.replay()
+    torch.cuda.synchronize()
+    got = [t.clone() for t in static_out]
+    want = step()
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert float((a - b).abs().max() / b.abs().max()) <= 1e-5
