@@ -131,15 +131,19 @@ __device__ __forceinline__ void sh_to_rgb(const float *__restrict__ row, const f
 struct RayGeom {
     float ox, oy, oz; // origin
     float dx, dy, dz; // unit direction
-    // The ranked face scan flushes subnormals (MUFU.RCP), so a front face whose dp = o.d is a positive
-    // subnormal would drop out of the ranking while the reference still divides by it.  Face offsets are
-    // fp16 values (|o_i| >= 2^-24 or 0), so every nonzero partial sum of dp is a multiple of
-    // 2^-34 * 2^-23 * min|d_i| over the nonzero d_i: with all nonzero |d_i| >= 2^-60 a nonzero dp is
-    // >= 2^-117, never subnormal.  Rays with a smaller nonzero direction component (pathological input)
-    // take the exact scan on every step instead.
-    bool exact_only;
 };
 
+// The ranked face scan flushes subnormals (MUFU.RCP), so a front face whose dp = o.d is a positive subnormal
+// would drop out of the ranking while the reference still divides by it.  Face offsets are fp16 values
+// (|o_i| >= 2^-24 or 0), so every nonzero partial sum of dp is a multiple of 2^-34 * 2^-23 * min|d_i| over the
+// nonzero d_i: with all nonzero |d_i| >= 2^-60 a nonzero dp is >= 2^-117, never subnormal.  Rays with a smaller
+// nonzero direction component (pathological input) must take the exact scan on every step instead.  Any test or
+// flag for that INSIDE the step loop of the recording forward costs 6-7 % (measured: a flag register, a second
+// loop instantiation selected per warp, a per-step test -- profiles/r02_forward_build_variants.json), so the
+// hot kernels come as twins: the fast one (ranked scan) raises a device flag when it meets such a ray and the
+// exact one, launched right behind it, re-does the launch only if the flag is up (ScanMode).  Kernels off the
+// hot path choose per ray (walk()).
+enum ScanMode { kScanFast = 0, kScanExactTwin = 1, kScanPerRay = 2 };
 __device__ __forceinline__ bool needs_exact_scan(float dx, float dy, float dz) {
     const float kTiny = 8.673617379884035e-19f; // 2^-60
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
@@ -244,10 +248,12 @@ struct PaddedFaces {
     // quotients are ordered the same way and no exact tie exists: the winner is the
     // reference's winner and t1 is its IEEE quotient.  Otherwise (near-ties, non-finite or
     // flushed values: rare) the row is rescanned exactly.
+    // EXACT_ONLY: the instantiation for rays the ranking is not proven for (needs_exact_scan()).
+    template <bool EXACT_ONLY = false>
     __device__ __forceinline__ void scan(uint32_t begin, uint32_t nf, float px, float py, float pz,
                                          const RayGeom &ray, float &t1, uint32_t &face) const {
         const float kInf = __int_as_float(0x7f800000);
-        if (ray.exact_only) {
+        if (EXACT_ONLY) {
             scan_exact(begin, nf, px, py, pz, ray, t1, face);
             return;
         }
@@ -321,7 +327,7 @@ struct PaddedFaces {
 // (point.xyz, density).  `cell_fn(cell, density, t0, t1, P, Pnext)` is called
 // for every cell with t1 > t0 and returns false to stop.  Returns n = cells
 // entered (max_steps + 1 when the budget ran out).
-template <typename Faces, typename CellFn>
+template <bool EXACT_ONLY, typename Faces, typename CellFn>
 __device__ __forceinline__ uint32_t walk(const Faces &fa, const float4 *__restrict__ cells,
                                          const RayGeom &ray, uint32_t start, uint32_t max_steps,
                                          CellFn &&cell_fn) {
@@ -337,7 +343,7 @@ __device__ __forceinline__ uint32_t walk(const Faces &fa, const float4 *__restri
         fa.row(cur, begin, nf);
         float t1 = __int_as_float(0x7f800000);
         uint32_t face = kNone;
-        fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+        fa.template scan<EXACT_ONLY>(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
         if (face == kNone)
             break;
         uint32_t nxt = fa.neighbour(begin, face);
@@ -510,22 +516,37 @@ struct BackwardRay {
     }
 };
 
+// the walk, with the scan variant chosen per ray (one-thread-per-ray kernels)
+template <typename Faces, typename CellFn>
+__device__ __forceinline__ uint32_t walk(const Faces &fa, const float4 *__restrict__ cells,
+                                         const RayGeom &ray, uint32_t start, uint32_t max_steps,
+                                         CellFn &&cell_fn) {
+    if (needs_exact_scan(ray.dx, ray.dy, ray.dz))
+        return walk<true>(fa, cells, ray, start, max_steps, cell_fn);
+    return walk<false>(fa, cells, ray, start, max_steps, cell_fn);
+}
+
 // ray index of this thread.  image_width == 0: linear.  Otherwise the rays are a
 // row-major image; a CTA covers a kTileW x kTileH pixel block (16x8 at 128 threads) and each
 // warp an 8x4 tile, so the lanes of a warp sit in the same or adjacent cells.
+// `block` is the tile this CTA works on: blockIdx.x, or a scheduled order of the tiles (backward replay).
 __device__ __forceinline__ bool thread_ray(uint32_t num_rays, uint32_t image_width,
-                                           uint32_t blocks_x, uint32_t &ray_idx) {
+                                           uint32_t blocks_x, uint32_t &ray_idx, uint32_t block) {
     if (image_width == 0) {
-        ray_idx = blockIdx.x * kBlock + threadIdx.x;
+        ray_idx = block * kBlock + threadIdx.x;
         return ray_idx < num_rays;
     }
-    uint32_t bx = blockIdx.x % blocks_x, by = blockIdx.x / blocks_x;
+    uint32_t bx = block % blocks_x, by = block / blocks_x;
     uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t x = bx * kTileW + (warp % kWarpsX) * 8 + (lane & 7);
     uint32_t y = by * kTileH + (warp / kWarpsX) * 4 + (lane >> 3);
     uint32_t height = num_rays / image_width;
     ray_idx = y * image_width + x;
     return x < image_width && y < height;
+}
+__device__ __forceinline__ bool thread_ray(uint32_t num_rays, uint32_t image_width,
+                                           uint32_t blocks_x, uint32_t &ray_idx) {
+    return thread_ray(num_rays, image_width, blocks_x, ray_idx, blockIdx.x);
 }
 
 } // namespace rfb

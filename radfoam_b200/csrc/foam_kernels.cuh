@@ -189,10 +189,17 @@ struct ForwardParams {
     float weight_threshold;
     uint32_t max_steps;
     int out_half;
+    uint32_t *exact_flag; // device word: raised by a fast kernel that met a ray outside the ranked scan's domain
 };
 
-template <int DEG, typename Faces>
+// MODE (ScanMode): kScanFast = ranked scan, raises *exact_flag for a ray it is not proven for; kScanExactTwin = the
+// same kernel with the exact scan, launched right behind the fast one, a no-op unless the flag is up (it then
+// overwrites every output); kScanPerRay = one launch that chooses per ray (used when `contrib` is accumulated
+// with atomics, which a second pass would double).
+template <int DEG, typename Faces, int MODE>
 __global__ void __launch_bounds__(kBlock) forward_kernel(const ForwardParams p, const Faces fa) {
+    if (MODE == kScanExactTwin && *p.exact_flag == 0u)
+        return;
     uint32_t r;
     if (!thread_ray(p.num_rays, p.image_width, p.blocks_x, r))
         return;
@@ -207,7 +214,8 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ForwardParams p, 
         ray.dy = __ldg(rp + 4);
         ray.dz = __ldg(rp + 5);
         normalize_dir(ray.dx, ray.dy, ray.dz);
-        ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
+        if (MODE == kScanFast && needs_exact_scan(ray.dx, ray.dy, ray.dz))
+            *p.exact_flag = 1u;
     }
     float sh[sh_dim(DEG)];
     sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
@@ -249,7 +257,9 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ForwardParams p, 
         return T > p.weight_threshold;
     };
 
-    uint32_t n = walk(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn);
+    uint32_t n = MODE == kScanPerRay
+                     ? walk(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn)
+                     : walk<MODE == kScanExactTwin>(fa, p.cells, ray, __ldg(p.start + r), p.max_steps, cell_fn);
 
     while (qi < Q) {
         p.qdepth[(uint64_t)r * Q + qi] = -1.0f;
@@ -291,21 +301,98 @@ struct Tape {
     uint32_t *ctrl;     // [0] bump cursor, [1] overflow flag
     uint32_t capacity;  // chunks in the pool
     uint32_t table_stride;
+    // Longest-first schedule of the replay: a ray is a serial chain of dependent loads (~1.5 us per step when
+    // the SM is nearly empty), so a 250-step ray that happens to sit in one of the LAST tiles the hardware
+    // dispatches keeps the kernel alive ~0.4 ms after everything else has drained -- 4 % of the backward on the
+    // full frame, 25 % on a 1/8 shard (ncu, profiles/r02_ncu_shard8.md).  After the recording forward,
+    // tile_steps_kernel takes each tile's longest record count from per_ray (a pass of its own: touching the
+    // forward kernel's epilogue for it cost 7 registers and an occupancy step), tape_order_kernel sorts the
+    // tiles by that, descending, and the replay's CTA b works on tile order[b]: the long chains start first
+    // and the short ones fill the tail.
+    uint32_t *tile_steps; // [blocks]
+    uint32_t *order;      // [blocks] tiles, longest first
 };
+
+// tile_steps[b] = max over the rays of tile b of the recorded step count (one warp per tile)
+__global__ void __launch_bounds__(256) tile_steps_kernel(const uint2 *__restrict__ per_ray, uint32_t num_rays,
+                                                         uint32_t image_width, uint32_t blocks_x, uint32_t blocks,
+                                                         uint32_t *__restrict__ tile_steps) {
+    const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (tile >= blocks)
+        return;
+    uint32_t longest = 0;
+    for (uint32_t t = lane; t < (uint32_t)kBlock; t += 32) { // thread t of the ray kernels' CTA `tile`
+        uint32_t r;
+        bool has;
+        if (image_width == 0) {
+            r = tile * kBlock + t;
+            has = r < num_rays;
+        } else {
+            const uint32_t bx = tile % blocks_x, by = tile / blocks_x, warp = t >> 5, l = t & 31;
+            const uint32_t x = bx * kTileW + (warp % kWarpsX) * 8 + (l & 7), y = by * kTileH + (warp / kWarpsX) * 4 + (l >> 3);
+            r = y * image_width + x;
+            has = x < image_width && y < num_rays / image_width;
+        }
+        if (has)
+            longest = max(longest, per_ray[r].x);
+    }
+    longest = __reduce_max_sync(0xffffffffu, longest);
+    if (lane == 0)
+        tile_steps[tile] = longest;
+}
+
+// counting sort of the tiles by recorded length, descending (one CTA; bins of one step, the last bin open-ended)
+constexpr int kOrderBins = 2048;
+__global__ void __launch_bounds__(1024) tape_order_kernel(const uint32_t *__restrict__ tile_steps, uint32_t blocks,
+                                                          uint32_t *__restrict__ order) {
+    __shared__ uint32_t bin_start[kOrderBins];
+    for (int i = threadIdx.x; i < kOrderBins; i += blockDim.x)
+        bin_start[i] = 0;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < blocks; b += blockDim.x)
+        atomicAdd(&bin_start[kOrderBins - 1 - min(tile_steps[b], (uint32_t)kOrderBins - 1)], 1u);  // longest -> bin 0
+    __syncthreads();
+    if (threadIdx.x < 32) { // exclusive scan of the 2048 counts by one warp, 64 bins per lane
+        uint32_t local = 0;
+        for (int i = 0; i < kOrderBins / 32; ++i)
+            local += bin_start[threadIdx.x * (kOrderBins / 32) + i];
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o)
+                incl += v;
+        }
+        uint32_t run = incl - local;
+        for (int i = 0; i < kOrderBins / 32; ++i) {
+            uint32_t c = bin_start[threadIdx.x * (kOrderBins / 32) + i];
+            bin_start[threadIdx.x * (kOrderBins / 32) + i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < blocks; b += blockDim.x)
+        order[atomicAdd(&bin_start[kOrderBins - 1 - min(tile_steps[b], (uint32_t)kOrderBins - 1)], 1u)] = b;
+}
 
 // Forward with an explicit warp-synchronous loop (all lanes stay in the loop until the warp is
 // done, so lane 0 can allocate tape chunks for the warp) that records the tape.
-template <int DEG, typename Faces>
-__global__ void __launch_bounds__(kBlock, 7 * 128 / kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
+// MODE: kScanFast / kScanExactTwin / kScanPerRay as for forward_kernel.  The twin allocates its tape chunks from a
+// cursor of its own (ctrl[2]), i.e. it re-uses the pool from the start and overwrites the fast kernel's table.
+template <int DEG, typename Faces, int MODE>
+__global__ void __launch_bounds__(kBlock) forward_record_kernel(const ForwardParams p, const Faces fa,
                                                                 const Tape tape) {
+    if (MODE == kScanExactTwin && *p.exact_flag == 0u)
+        return;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int CURSOR = MODE == kScanExactTwin ? 2 : 0;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gwarp = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     uint32_t r;
     bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
     const bool has_ray = !done;
 
-    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, false};
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
     float sh[sh_dim(DEG)];
     uint32_t Q = 0, qi = 0;
     const float *qv = nullptr;
@@ -321,7 +408,6 @@ __global__ void __launch_bounds__(kBlock, 7 * 128 / kBlock) forward_record_kerne
         ray.dy = __ldg(rp + 4);
         ray.dz = __ldg(rp + 5);
         normalize_dir(ray.dx, ray.dy, ray.dz);
-        ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
         Q = p.quantiles ? p.num_q : 0u;
         qv = p.quantiles + (uint64_t)r * p.num_q;
         cq = Q ? __ldg(qv) : 0.0f;
@@ -333,11 +419,14 @@ __global__ void __launch_bounds__(kBlock, 7 * 128 / kBlock) forward_record_kerne
     float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, t0 = 0.0f;
     uint32_t n = 0, nrec = 0;
     uint32_t chunk = kTapeNoChunk;
+    // the step loop, instantiated for the ranked scan and (warps holding a ray it is not proven for) the exact one
+    if (MODE == kScanFast && has_ray && needs_exact_scan(ray.dx, ray.dy, ray.dz))
+        *p.exact_flag = 1u;
     for (uint32_t k = 0;; ++k) {
         if ((k % kTapeChunk) == 0) { // the warp enters a new chunk of steps
             uint32_t c = kTapeNoChunk;
             if (lane == 0) {
-                c = atomicAdd(tape.ctrl, 1u);
+                c = atomicAdd(tape.ctrl + CURSOR, 1u);
                 if (c >= tape.capacity || k / kTapeChunk >= tape.table_stride) {
                     atomicExch(tape.ctrl + 1, 1u);
                     c = kTapeNoChunk;
@@ -356,7 +445,10 @@ __global__ void __launch_bounds__(kBlock, 7 * 128 / kBlock) forward_record_kerne
                 fa.row(cur, begin, nf);
                 float t1 = __int_as_float(0x7f800000);
                 uint32_t face = kNone;
-                fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                if (MODE == kScanPerRay && needs_exact_scan(ray.dx, ray.dy, ray.dz))
+                    fa.template scan<true>(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                else
+                    fa.template scan<MODE == kScanExactTwin>(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
                 if (face == kNone) {
                     done = true;
                 } else {
@@ -460,7 +552,6 @@ __device__ __forceinline__ void backward_ray_setup(const BackwardParams &p, uint
     ray.dy = __ldg(rp + 4);
     ray.dz = __ldg(rp + 5);
     normalize_dir(ray.dx, ray.dy, ray.dz);
-        ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
     sh_basis<DEG>(ray.dx, ray.dy, ray.dz, sh);
     st.err = 0.0f;
     if (p.io_half) {
@@ -603,15 +694,16 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS * 128 / kBlock)
         tags[i] = kNone;
     __syncwarp();
 
+    constexpr bool replay = REPLAY;
+    const uint32_t tile = (replay && tape.order) ? tape.order[blockIdx.x] : blockIdx.x; // longest tiles first
     uint32_t r;
-    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r);
-    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, false};
+    bool done = !thread_ray(p.num_rays, p.image_width, p.blocks_x, r, tile);
+    RayGeom ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
     float sh[sh_dim(DEG)];
     BackwardRay st;
     uint32_t cur = 0;
     float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr bool replay = REPLAY;
-    const uint32_t gwarp = blockIdx.x * (kBlock / 32) + warp;
+    const uint32_t gwarp = tile * (kBlock / 32) + warp;
     uint32_t nrec = 0, last_cell = 0;
     uint2 rec = make_uint2(0u, 0u); // record of the step about to be processed (replay)
     if (!done) {
@@ -679,7 +771,10 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS * 128 / kBlock)
                 uint32_t begin, nf;
                 fa.row(cur, begin, nf);
                 uint32_t face = kNone;
-                fa.scan(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                if (needs_exact_scan(ray.dx, ray.dy, ray.dz)) // re-walk is the fallback path: tested per step
+                    fa.template scan<true>(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
+                else
+                    fa.template scan<false>(begin, nf, pc.x, pc.y, pc.z, ray, t1, face);
                 if (face == kNone) {
                     done = true;
                 } else {
@@ -1210,7 +1305,6 @@ __device__ __forceinline__ void cast_ray(const CameraParams &c, int i, int j, Ra
     ray.dx = __fmul_rn(d[0], mask);
     ray.dy = __fmul_rn(d[1], mask);
     ray.dz = __fmul_rn(d[2], mask);
-    ray.exact_only = needs_exact_scan(ray.dx, ray.dy, ray.dz);
 }
 
 // make_rgba8 (tracing_utils.cuh:105-115): clamp, truncate
@@ -1233,10 +1327,13 @@ struct BenchmarkParams {
     uint32_t blocks_x;
     float weight_threshold;
     uint32_t max_steps;
+    uint32_t *exact_flag;
 };
 
-template <int DEG, typename Faces>
+template <int DEG, typename Faces, int MODE>
 __global__ void __launch_bounds__(kBlock) benchmark_kernel(const BenchmarkParams p, const Faces fa) {
+    if (MODE == kScanExactTwin && *p.exact_flag == 0u)
+        return;
     uint32_t r;
     if (!thread_ray(p.cam.width * p.cam.height, p.cam.width, p.blocks_x, r))
         return;
@@ -1265,7 +1362,9 @@ __global__ void __launch_bounds__(kBlock) benchmark_kernel(const BenchmarkParams
         T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         return T > p.weight_threshold;
     };
-    walk(fa, p.cells, ray, __ldg(p.start), p.max_steps, cell_fn);
+    if (MODE == kScanFast && needs_exact_scan(ray.dx, ray.dy, ray.dz))
+        *p.exact_flag = 1u;
+    walk<MODE == kScanExactTwin>(fa, p.cells, ray, __ldg(p.start), p.max_steps, cell_fn);
     p.out[r] = pack_rgba8(cr, cg, cb, 1.0f);
 }
 

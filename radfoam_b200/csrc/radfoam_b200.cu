@@ -124,7 +124,9 @@ struct rfb_pipeline {
     rfb_scene_params params = {nullptr, nullptr, nullptr, 1.0f};
     bool params_bound = false;
     // walk tape (forward records, backward replays; see foam_kernels.cuh)
-    DeviceBuffer tape_pool, tape_table, tape_per_ray, tape_ctrl;
+    DeviceBuffer scan_flag; // one word: a fast forward met a ray outside the ranked scan's domain (ScanMode)
+    DeviceBuffer tape_pool, tape_table, tape_per_ray, tape_ctrl, tape_sched; // sched: [tile_steps | order]
+    uint32_t tape_blocks = 0;
     uint32_t tape_capacity = 0;      // chunks
     uint32_t tape_table_stride = 0;
     bool tape_valid = false;
@@ -320,14 +322,37 @@ int profile_mark(rfb_pipeline *p, int which, cudaStream_t stream) {
     return 0;
 }
 
-template <typename Faces>
-int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t blocks,
-                   cudaStream_t stream) {
+template <typename Faces, int MODE>
+int launch_forward_mode(int deg, const ForwardParams &fp, const Faces &fa, uint32_t blocks, cudaStream_t stream) {
     switch (deg) {
-    case 0: RFB_LAUNCH((forward_kernel<0, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
-    case 1: RFB_LAUNCH((forward_kernel<1, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
-    case 2: RFB_LAUNCH((forward_kernel<2, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
-    default: RFB_LAUNCH((forward_kernel<3, Faces>), blocks, kBlock, 0, stream, fp, fa); break;
+    case 0: RFB_LAUNCH((forward_kernel<0, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa); break;
+    case 1: RFB_LAUNCH((forward_kernel<1, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa); break;
+    case 2: RFB_LAUNCH((forward_kernel<2, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa); break;
+    default: RFB_LAUNCH((forward_kernel<3, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa); break;
+    }
+    RFB_LAUNCHED();
+    return 0;
+}
+
+// The fast kernel and, right behind it, its exact twin (a no-op unless the fast one raised the flag); with a
+// contribution output (accumulated by atomics: a second pass would double it) one launch that chooses per ray.
+template <typename Faces>
+int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t blocks, cudaStream_t stream) {
+    if (fp.contrib)
+        return launch_forward_mode<Faces, kScanPerRay>(deg, fp, fa, blocks, stream);
+    if (int rc = launch_forward_mode<Faces, kScanFast>(deg, fp, fa, blocks, stream))
+        return rc;
+    return launch_forward_mode<Faces, kScanExactTwin>(deg, fp, fa, blocks, stream);
+}
+
+template <typename Faces, int MODE>
+int launch_forward_record_mode(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape, uint32_t blocks,
+                               cudaStream_t stream) {
+    switch (deg) {
+    case 0: RFB_LAUNCH((forward_record_kernel<0, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa, tape); break;
+    case 1: RFB_LAUNCH((forward_record_kernel<1, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa, tape); break;
+    case 2: RFB_LAUNCH((forward_record_kernel<2, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa, tape); break;
+    default: RFB_LAUNCH((forward_record_kernel<3, Faces, MODE>), blocks, kBlock, 0, stream, fp, fa, tape); break;
     }
     RFB_LAUNCHED();
     return 0;
@@ -336,14 +361,11 @@ int launch_forward(int deg, const ForwardParams &fp, const Faces &fa, uint32_t b
 template <typename Faces>
 int launch_forward_record(int deg, const ForwardParams &fp, const Faces &fa, const Tape &tape,
                           uint32_t blocks, cudaStream_t stream) {
-    switch (deg) {
-    case 0: RFB_LAUNCH((forward_record_kernel<0, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
-    case 1: RFB_LAUNCH((forward_record_kernel<1, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
-    case 2: RFB_LAUNCH((forward_record_kernel<2, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
-    default: RFB_LAUNCH((forward_record_kernel<3, Faces>), blocks, kBlock, 0, stream, fp, fa, tape); break;
-    }
-    RFB_LAUNCHED();
-    return 0;
+    if (fp.contrib)
+        return launch_forward_record_mode<Faces, kScanPerRay>(deg, fp, fa, tape, blocks, stream);
+    if (int rc = launch_forward_record_mode<Faces, kScanFast>(deg, fp, fa, tape, blocks, stream))
+        return rc;
+    return launch_forward_record_mode<Faces, kScanExactTwin>(deg, fp, fa, tape, blocks, stream);
 }
 
 // Size / reset the tape for a recording forward of `blocks` CTAs; fills `tape`.  The tape is an optimisation:
@@ -357,7 +379,7 @@ int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t m
     // grow the pool if the previous recording needed more chunks than it had
     if (p->tape_readback_pending && cudaEventQuery(p->tape_readback_done) == cudaSuccess) {
         p->tape_readback_pending = false;
-        uint32_t wanted = p->tape_readback[0];
+        uint32_t wanted = p->tape_readback[0] > p->tape_readback[2] ? p->tape_readback[0] : p->tape_readback[2];
         if (wanted > p->tape_capacity)
             p->tape_capacity = wanted + wanted / 4;
     }
@@ -382,12 +404,16 @@ int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t m
     if (p->tape_capacity < want || p->tape_pool.ensure(pool_bytes) != cudaSuccess ||
         p->tape_table.ensure((size_t)num_warps * stride * sizeof(uint32_t)) != cudaSuccess ||
         p->tape_per_ray.ensure((size_t)num_rays * sizeof(uint2)) != cudaSuccess ||
+        p->tape_sched.ensure((size_t)blocks * 2 * sizeof(uint32_t)) != cudaSuccess ||
         p->tape_ctrl.ensure(4 * sizeof(uint32_t)) != cudaSuccess) {
         cudaGetLastError(); // out of memory is not sticky; forget it
         p->tape_capacity = 0; // start from the first guess next time
         return 0;
     }
     RFB_CUDA(cudaMemsetAsync(p->tape_ctrl.ptr, 0, 4 * sizeof(uint32_t), stream));
+    p->tape_blocks = blocks;
+    tape.tile_steps = reinterpret_cast<uint32_t *>(p->tape_sched.ptr);
+    tape.order = tape.tile_steps + blocks;
     if (!p->tape_readback) {
         RFB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->tape_readback), 4 * sizeof(uint32_t)));
         RFB_CUDA(cudaEventCreateWithFlags(&p->tape_readback_done, cudaEventDisableTiming));
@@ -471,17 +497,23 @@ int launch_backward_cached(int deg, const BackwardParams &bp, const Faces &fa, c
     }
 }
 
-template <typename Faces>
-int launch_benchmark(int deg, const BenchmarkParams &bp, const Faces &fa, uint32_t blocks,
-                     cudaStream_t stream) {
+template <typename Faces, int MODE>
+int launch_benchmark_mode(int deg, const BenchmarkParams &bp, const Faces &fa, uint32_t blocks, cudaStream_t stream) {
     switch (deg) {
-    case 0: RFB_LAUNCH((benchmark_kernel<0, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
-    case 1: RFB_LAUNCH((benchmark_kernel<1, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
-    case 2: RFB_LAUNCH((benchmark_kernel<2, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
-    default: RFB_LAUNCH((benchmark_kernel<3, Faces>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 0: RFB_LAUNCH((benchmark_kernel<0, Faces, MODE>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 1: RFB_LAUNCH((benchmark_kernel<1, Faces, MODE>), blocks, kBlock, 0, stream, bp, fa); break;
+    case 2: RFB_LAUNCH((benchmark_kernel<2, Faces, MODE>), blocks, kBlock, 0, stream, bp, fa); break;
+    default: RFB_LAUNCH((benchmark_kernel<3, Faces, MODE>), blocks, kBlock, 0, stream, bp, fa); break;
     }
     RFB_LAUNCHED();
     return 0;
+}
+
+template <typename Faces>
+int launch_benchmark(int deg, const BenchmarkParams &bp, const Faces &fa, uint32_t blocks, cudaStream_t stream) {
+    if (int rc = launch_benchmark_mode<Faces, kScanFast>(deg, bp, fa, blocks, stream))
+        return rc;
+    return launch_benchmark_mode<Faces, kScanExactTwin>(deg, bp, fa, blocks, stream);
 }
 
 rfb_trace_settings settings_or_default(const rfb_trace_settings *s) {
@@ -531,7 +563,9 @@ void rfb_destroy_pipeline(rfb_pipeline *p) {
     p->faces.release();
     p->nbr.release();
     p->acc.release();
+    p->scan_flag.release();
     p->tape_pool.release();
+    p->tape_sched.release();
     p->tape_table.release();
     p->tape_per_ray.release();
     p->tape_ctrl.release();
@@ -566,7 +600,7 @@ int rfb_tape_status(rfb_pipeline *p, uint32_t *capacity_chunks, uint32_t *used_c
         return fail("rfb_tape_status: no recorded tape");
     RFB_CUDA(cudaEventSynchronize(p->tape_readback_done));
     *capacity_chunks = p->tape_capacity;
-    *used_chunks = p->tape_readback[0];
+    *used_chunks = p->tape_readback[0] > p->tape_readback[2] ? p->tape_readback[0] : p->tape_readback[2];
     *overflowed = p->tape_readback[1];
     return 0;
 }
@@ -755,6 +789,9 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     fa.faces = reinterpret_cast<const uint2 *>(p->faces.ptr);
     fa.nbr = reinterpret_cast<const uint32_t *>(p->nbr.ptr);
     fa.off = point_adjacency_offsets;
+    RFB_CUDA(p->scan_flag.ensure(4 * sizeof(uint32_t)));
+    RFB_CUDA(cudaMemsetAsync(p->scan_flag.ptr, 0, 4 * sizeof(uint32_t), stream));
+    fp.exact_flag = reinterpret_cast<uint32_t *>(p->scan_flag.ptr);
     bool record = opts && (opts->flags & RFB_FLAG_RECORD_TAPE) && opts->scene_version != 0;
     p->tape_valid = false;
     Tape tape = {};
@@ -769,8 +806,14 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     if (int rc = profile_mark(p, 1, stream))
         return rc;
     if (record) {
+        // the replay's longest-first schedule, from the step counts the kernel above just recorded
+        RFB_LAUNCH((tile_steps_kernel), (blocks + 7) / 8, 256, 0, stream, (const uint2 *)tape.per_ray, num_rays,
+                   fp.image_width, fp.blocks_x, blocks, tape.tile_steps);
+        RFB_LAUNCH((tape_order_kernel), 1, 1024, 0, stream, (const uint32_t *)tape.tile_steps, blocks, tape.order);
+        g_launches += 1;
+        RFB_LAUNCHED();
         if (!capturing(stream)) {
-            RFB_CUDA(cudaMemcpyAsync(p->tape_readback, p->tape_ctrl.ptr, 2 * sizeof(uint32_t),
+            RFB_CUDA(cudaMemcpyAsync(p->tape_readback, p->tape_ctrl.ptr, 4 * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, stream));
             RFB_CUDA(cudaEventRecord(p->tape_readback_done, stream));
             p->tape_readback_pending = true;
@@ -871,6 +914,9 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
         tape.ctrl = reinterpret_cast<uint32_t *>(p->tape_ctrl.ptr);
         tape.capacity = p->tape_capacity;
         tape.table_stride = p->tape_table_stride;
+        tape.tile_steps = reinterpret_cast<uint32_t *>(p->tape_sched.ptr);
+        const char *sched = getenv("RFB_REPLAY_ORDER"); // "0": dispatch order (for measuring the schedule's effect)
+        tape.order = (blocks == p->tape_blocks && !(sched && sched[0] == '0')) ? tape.tile_steps + blocks : nullptr;
         if (int rc = wait_for(p->tape_ready, p->tape_stream, stream))
             return rc;
     }
@@ -1093,6 +1139,9 @@ int rfb_trace_benchmark(rfb_pipeline *p, const rfb_trace_settings *settings, uin
     bp.cam.model = camera->model;
     bp.weight_threshold = s.weight_threshold;
     bp.max_steps = s.max_intersections;
+    RFB_CUDA(p->scan_flag.ensure(4 * sizeof(uint32_t)));
+    RFB_CUDA(cudaMemsetAsync(p->scan_flag.ptr, 0, 4 * sizeof(uint32_t), stream));
+    bp.exact_flag = reinterpret_cast<uint32_t *>(p->scan_flag.ptr);
     bp.blocks_x = (camera->width + kTileW - 1) / kTileW;
     uint32_t blocks = bp.blocks_x * ((camera->height + kTileH - 1) / kTileH);
     // the caller's offsets, re-laid-out (copied, not recomputed) into the padded face rows

@@ -385,6 +385,12 @@ inline unsigned atomicCAS(unsigned *p, unsigned expected, unsigned desired) {
     __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
     return expected; // the old value either way
 }
+inline unsigned atomicMax(unsigned *p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
 inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline void rfb_emu_red_add_v4(float *p, float a, float b, float c, float d) {
     emu::counters.red_v4.fetch_add(1, std::memory_order_relaxed);
@@ -454,6 +460,15 @@ inline T __shfl_down_sync(unsigned mask, T value, unsigned delta, int width = 32
     if ((lane & (unsigned)(width - 1)) + delta >= (unsigned)width || !(mask >> from & 1u))
         return value;
     return emu::from_bits<T>(v[from]);
+}
+
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T value, unsigned delta, int width = 32) {
+    auto v = emu::gather(mask, emu::to_bits(value));
+    const unsigned lane = emu::cur->t.lane;
+    if ((lane & (unsigned)(width - 1)) < delta || !(mask >> (lane - delta) & 1u))
+        return value;
+    return emu::from_bits<T>(v[lane - delta]);
 }
 
 // ---- runtime API (synchronous stand-ins; every handle is a dummy)

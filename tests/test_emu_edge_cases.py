@@ -131,3 +131,36 @@ def test_camera_inside_the_foam_without_quantiles(base):
     rays = foam.pinhole_rays(40, 24, pos, target=(1, 0.3, 0.2), fov=1.4)
     start = np.full((24, 40), foam.nearest_point(f.points, pos), dtype=np.uint32)
     compare(f, rays, start, None)
+
+
+def test_tiny_direction_components_take_the_exact_twin(base):
+    """Rays with a nonzero direction component below 2^-60 are outside the domain the ranked face scan is proven
+    for (a front face's dp can be a positive subnormal, which MUFU.RCP flushes): the fast kernel raises the device
+    flag and the exact twin re-does the launch -- plain forward, recording forward + replay, contribution
+    (per-ray dispatch) and the benchmark kernel must all agree with the oracle, other rays of the batch included."""
+    f = base.foam
+    rays = base.rays.copy()
+    rays[3, 5, 3:] = [1.0, 1e-30, 0.0]       # axis-aligned but for a denormal-sized component
+    rays[9, 17, 3:] = [3e-25, -1.0, 2e-22]
+    rays[20, 2, 3:] = [0.0, 0.0, 1.0]        # exactly axis-aligned: zeros are fine, stays on the fast path
+    got = compare(f, rays, base.start, base.quantiles)
+    scene = (f.points, f.attributes, f.adjacency, f.offsets)
+    ref = oracle.trace_forward(*scene, rays, base.start, base.quantiles, return_contribution=True)
+    pipe = emu.EmuPipeline(f.sh_degree)
+    con = pipe.trace_forward(*scene, rays, base.start, base.quantiles, return_contribution=True)
+    assert np.array_equal(con["num_intersections"].reshape(-1), np.asarray(ref["num_intersections"]).reshape(-1))
+    assert common.grad_error(con["contribution"], np.asarray(ref["contribution"], dtype=np.float32)) <= 1e-5
+    # recording forward (twice: the second one has a pool large enough) + replaying backward
+    for _ in range(2):
+        rec = pipe.trace_forward(*scene, rays, base.start, base.quantiles, scene_version=3, record_tape=True)
+    assert not pipe.tape_status()["overflowed"]
+    for k in ("num_intersections", "depth_indices"):
+        assert np.array_equal(rec[k], got[k]), k
+    assert np.array_equal(rec["rgba"].view(np.uint32), got["rgba"].view(np.uint32))
+    g, gd = base.grad_rgba, base.grad_depth
+    rb = oracle.trace_backward(*scene, rays, base.start, np.asarray(ref["rgba"]), g, base.quantiles,
+                               np.asarray(ref["depth_indices"]), gd)
+    bwd = pipe.trace_backward(*(None,) * 6, rec["rgba"], g, None, rec["depth_indices"], gd, scene_version=3,
+                              use_tape=True)
+    for k in ("points_grad", "attr_grad"):
+        assert common.grad_error(bwd[k], np.asarray(rb[k])) <= 2e-5, k

@@ -209,7 +209,9 @@ def test_parameter_form_scene_equals_torch_glue(torch_cuda, attr_dtype):
     for name, ga, gb in zip(("points", "att_dc", "att_sh", "density"), a["grads"], b["grads"]):
         assert ga.shape == gb.shape
         err = float((ga - gb).abs().max() / ga.abs().max().clamp_min(1e-30))
-        assert err <= 1e-5, f"{name}: {err:.3g}"
+        # fp16 pipelines round the attribute gradient to half once (1e-3 relative); the two runs sum their fp32
+        # accumulators in different atomic orders, so the rounded values may differ by one half-ulp
+        assert err <= (1e-5 if attr_dtype == "float32" or name == "points" else 2e-3), f"{name}: {err:.3g}"
 
 
 def test_training_step_is_cuda_graph_capturable(torch_cuda):
