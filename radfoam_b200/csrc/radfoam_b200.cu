@@ -377,7 +377,8 @@ int prepare_tape(rfb_pipeline *p, uint32_t blocks, uint32_t num_rays, uint32_t m
     const uint32_t num_warps = blocks * (kBlock / 32);
     const uint32_t stride = max_steps / kTapeChunk + 2;
     // grow the pool if the previous recording needed more chunks than it had
-    if (p->tape_readback_pending && cudaEventQuery(p->tape_readback_done) == cudaSuccess) {
+    // (no event query while a graph is being captured: "unsafe" runtime calls invalidate a global-mode capture)
+    if (p->tape_readback_pending && !capturing(stream) && cudaEventQuery(p->tape_readback_done) == cudaSuccess) {
         p->tape_readback_pending = false;
         uint32_t wanted = p->tape_readback[0] > p->tape_readback[2] ? p->tape_readback[0] : p->tape_readback[2];
         if (wanted > p->tape_capacity)
