@@ -341,14 +341,16 @@ __global__ void __launch_bounds__(256) tile_steps_kernel(const uint2 *__restrict
         tile_steps[tile] = longest;
 }
 
-// The replay's tile order (one CTA): the longest 1/16 of the tiles first, by descending length (counting sort,
-// bins of one step, the last bin open-ended), then all the others in their original, spatially coherent order.
-// (Sorting ALL tiles by length was measured: it removes the tail but scatters neighbouring tiles in time, and
-// the lost L2 sharing of cells and gradient rows costs more than the tail on a full frame -- 11.1 vs 10.35 ms;
-// 1.83 vs 1.96 ms on a 1/8 shard.  profiles/r02_replay_schedule.json)
+// The replay's tile order (one CTA): the `budget` longest tiles first, by descending length (counting sort, bins
+// of one step, the last bin open-ended; whole bins only), then all the others in their original, spatially
+// coherent order.  Measured (profiles/r02_replay_schedule.json): sorting ALL tiles removes most of the tail but
+// scatters neighbouring tiles in time, and the lost L2 sharing of cells and gradient rows costs more than the tail
+// on a full frame (11.1 vs 10.35 ms) while it pays on a 1/8 shard (1.83 vs 1.96 ms), where the launch is fewer
+// than three waves of CTAs whose durations differ 2.4x.  So the host sorts everything for launches of up to 8 waves
+// and keeps the dispatch order (no schedule at all) above that.
 constexpr int kOrderBins = 2048;
 __global__ void __launch_bounds__(1024) tape_order_kernel(const uint32_t *__restrict__ tile_steps, uint32_t blocks,
-                                                          uint32_t *__restrict__ order) {
+                                                          uint32_t budget, uint32_t *__restrict__ order) {
     __shared__ uint32_t bin_start[kOrderBins];
     __shared__ uint32_t warp_total[32];
     __shared__ uint32_t s_cut, s_running;
@@ -373,7 +375,6 @@ __global__ void __launch_bounds__(1024) tape_order_kernel(const uint32_t *__rest
                 incl += v;
         }
         uint32_t run = incl - local;
-        const uint32_t budget = blocks / 16u;
         uint32_t my_cut = 0, my_long = 0; // bins [0, my_cut) are long; their tile count
         for (int i = 0; i < PER; ++i) {
             const uint32_t c = bin_start[lane * PER + i];
@@ -1035,7 +1036,9 @@ struct PeerReduceParams {
     int scrub;
 };
 
-template <int DEG, typename AttrT>
+// WORLD > 0: the number of ranks as a compile-time constant (2, 4, 8: exactly that many loads per thread in
+// flight and no more registers than that needs, so more CTAs fit an SM); WORLD == 0: any world up to kMaxPeers.
+template <int DEG, typename AttrT, int WORLD>
 __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerReduceParams p) {
     constexpr int GR = grad_row(DEG), SR = sh_row(DEG), A = attr_dim(DEG);
     constexpr int ROW_VECS = GR / 4;                 // float4 per accumulator row
@@ -1052,15 +1055,17 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
         const uint32_t nrows = min((uint32_t)kPeerRows, p.num_points - row0);
         if (t < nrows * ROW_VECS) {
             const uint64_t off = (uint64_t)row0 * GR + 4ull * t;
-            float4 v[kMaxPeers];
+            constexpr int SLOTS = WORLD > 0 ? WORLD : kMaxPeers;
+            const int world = WORLD > 0 ? WORLD : (int)p.world;
+            float4 v[SLOTS];
 #pragma unroll
-            for (int w = 0; w < kMaxPeers; ++w)
-                if (w < (int)p.world)
+            for (int w = 0; w < SLOTS; ++w)
+                if (w < world)
                     v[w] = *reinterpret_cast<const float4 *>(p.acc[w] + off);
             float4 s = v[0];
 #pragma unroll
-            for (int w = 1; w < kMaxPeers; ++w)
-                if (w < (int)p.world) {
+            for (int w = 1; w < SLOTS; ++w)
+                if (w < world) {
                     s.x += v[w].x;
                     s.y += v[w].y;
                     s.z += v[w].z;

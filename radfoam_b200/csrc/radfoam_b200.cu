@@ -127,6 +127,7 @@ struct rfb_pipeline {
     DeviceBuffer scan_flag; // one word: a fast forward met a ray outside the ranked scan's domain (ScanMode)
     DeviceBuffer tape_pool, tape_table, tape_per_ray, tape_ctrl, tape_sched; // sched: [tile_steps | order]
     uint32_t tape_blocks = 0;
+    bool tape_scheduled = false; // the last recording forward also built a tile order for the replay
     uint32_t tape_capacity = 0;      // chunks
     uint32_t tape_table_stride = 0;
     bool tape_valid = false;
@@ -807,12 +808,17 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
     if (int rc = profile_mark(p, 1, stream))
         return rc;
     if (record) {
-        // the replay's longest-first schedule, from the step counts the kernel above just recorded
-        RFB_LAUNCH((tile_steps_kernel), (blocks + 7) / 8, 256, 0, stream, (const uint2 *)tape.per_ray, num_rays,
-                   fp.image_width, fp.blocks_x, blocks, tape.tile_steps);
-        RFB_LAUNCH((tape_order_kernel), 1, 1024, 0, stream, (const uint32_t *)tape.tile_steps, blocks, tape.order);
-        g_launches += 1;
-        RFB_LAUNCHED();
+        // the replay's longest-first schedule (small launches only: see tape_order_kernel)
+        const char *sched = getenv("RFB_REPLAY_ORDER"); // "0" never, "1" always (for measuring)
+        p->tape_scheduled = sched ? sched[0] == '1' : blocks <= 148u * 5u * 8u;
+        if (p->tape_scheduled) {
+            RFB_LAUNCH((tile_steps_kernel), (blocks + 7) / 8, 256, 0, stream, (const uint2 *)tape.per_ray, num_rays,
+                       fp.image_width, fp.blocks_x, blocks, tape.tile_steps);
+            RFB_LAUNCH((tape_order_kernel), 1, 1024, 0, stream, (const uint32_t *)tape.tile_steps, blocks, blocks,
+                       tape.order);
+            g_launches += 1;
+            RFB_LAUNCHED();
+        }
         if (!capturing(stream)) {
             RFB_CUDA(cudaMemcpyAsync(p->tape_readback, p->tape_ctrl.ptr, 4 * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, stream));
@@ -916,8 +922,7 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
         tape.capacity = p->tape_capacity;
         tape.table_stride = p->tape_table_stride;
         tape.tile_steps = reinterpret_cast<uint32_t *>(p->tape_sched.ptr);
-        const char *sched = getenv("RFB_REPLAY_ORDER"); // "0": dispatch order (for measuring the schedule's effect)
-        tape.order = (blocks == p->tape_blocks && !(sched && sched[0] == '0')) ? tape.tile_steps + blocks : nullptr;
+        tape.order = (blocks == p->tape_blocks && p->tape_scheduled) ? tape.tile_steps + blocks : nullptr;
         if (int rc = wait_for(p->tape_ready, p->tape_stream, stream))
             return rc;
     }
@@ -977,18 +982,33 @@ int rfb_reduce_finalize_peers(rfb_pipeline *p, uint32_t world, uint32_t rank, ui
     const uint32_t mine = (num_blocks + world - 1 - rank) / world;
     if (mine == 0)
         return 0;
-    int grid = (int)(mine < 148u * 8u ? mine : 148u * 8u);
+    int grid = (int)(mine < 148u * 16u ? mine : 148u * 16u);
     cudaStream_t stream = (cudaStream_t)stream_;
-    switch (p->sh_degree * 2 + (p->attr_dtype == RFB_FLOAT16 ? 1 : 0)) {
-    case 0: RFB_LAUNCH((reduce_finalize_peers_kernel<0, float>), grid, 256, 0, stream, pr); break;
-    case 1: RFB_LAUNCH((reduce_finalize_peers_kernel<0, __half>), grid, 256, 0, stream, pr); break;
-    case 2: RFB_LAUNCH((reduce_finalize_peers_kernel<1, float>), grid, 256, 0, stream, pr); break;
-    case 3: RFB_LAUNCH((reduce_finalize_peers_kernel<1, __half>), grid, 256, 0, stream, pr); break;
-    case 4: RFB_LAUNCH((reduce_finalize_peers_kernel<2, float>), grid, 256, 0, stream, pr); break;
-    case 5: RFB_LAUNCH((reduce_finalize_peers_kernel<2, __half>), grid, 256, 0, stream, pr); break;
-    case 6: RFB_LAUNCH((reduce_finalize_peers_kernel<3, float>), grid, 256, 0, stream, pr); break;
-    default: RFB_LAUNCH((reduce_finalize_peers_kernel<3, __half>), grid, 256, 0, stream, pr); break;
+    const bool half = p->attr_dtype == RFB_FLOAT16;
+#define RFB_PEER_LAUNCH(DEG, W)                                                                          \
+    do {                                                                                                 \
+        if (half)                                                                                        \
+            RFB_LAUNCH((reduce_finalize_peers_kernel<DEG, __half, W>), grid, 256, 0, stream, pr);        \
+        else                                                                                             \
+            RFB_LAUNCH((reduce_finalize_peers_kernel<DEG, float, W>), grid, 256, 0, stream, pr);         \
+    } while (0)
+#define RFB_PEER_WORLD(DEG)                                                                              \
+    do {                                                                                                 \
+        switch (world) {                                                                                 \
+        case 2: RFB_PEER_LAUNCH(DEG, 2); break;                                                          \
+        case 4: RFB_PEER_LAUNCH(DEG, 4); break;                                                          \
+        case 8: RFB_PEER_LAUNCH(DEG, 8); break;                                                          \
+        default: RFB_PEER_LAUNCH(DEG, 0); break;                                                         \
+        }                                                                                                \
+    } while (0)
+    switch (p->sh_degree) {
+    case 0: RFB_PEER_WORLD(0); break;
+    case 1: RFB_PEER_WORLD(1); break;
+    case 2: RFB_PEER_WORLD(2); break;
+    default: RFB_PEER_WORLD(3); break;
     }
+#undef RFB_PEER_WORLD
+#undef RFB_PEER_LAUNCH
     RFB_LAUNCHED();
     return 0;
 }

@@ -108,11 +108,13 @@ def small_foam(num_points: int = 256, sh_degree: int = 3, seed: int = 0) -> Foam
     return Foam(pts, attrs, adj, off, sh_degree)
 
 
-def scene_foam(num_points: int, sh_degree: int = 3, seed: int | None = None) -> Foam:
+def scene_foam(num_points: int, sh_degree: int = 3, seed: int | None = None, adjacency=None) -> Foam:
     """Configs 2-5 recipe: 70% of the points on a unit-sphere shell
     (radial noise sigma 0.01, dense), 25% ~U[-1.5,1.5]^3, 5% far field ~N(0,8^2)
     (both nearly empty), so rays from outside mostly terminate at the shell after
-    O(10^2) cells and some run to the hull."""
+    O(10^2) cells and some run to the hull.
+    ``adjacency`` = ``(adjacency, offsets)`` of an earlier build of the SAME foam (same arguments) skips the
+    Delaunay triangulation -- the only slow part; everything else is regenerated from the seed."""
     seed = num_points if seed is None else seed
     rng = np.random.default_rng(seed)
     n_surf = int(0.70 * num_points)
@@ -137,52 +139,39 @@ def scene_foam(num_points: int, sh_degree: int = 3, seed: int | None = None) -> 
                     10.0 * softplus_beta10(rng.normal(1.0, 1.0, size=n)),
                     softplus_beta10(rng.normal(-1.0, 0.5, size=n))).astype(np.float32)
     attrs = make_attributes(rng, n, sh_degree, dens)
-    adj, off = delaunay_adjacency(pts)
+    if adjacency is not None:
+        adj, off = (np.ascontiguousarray(a, dtype=np.uint32) for a in adjacency)
+        if off.shape[0] != n + 1 or int(off[-1]) != adj.shape[0]:
+            raise RuntimeError("the given adjacency does not belong to this foam")
+    else:
+        adj, off = delaunay_adjacency(pts)
     return Foam(pts, attrs, adj, off, sh_degree)
 
 
-def pinhole_rays(width: int, height: int, position, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0),
-                 fov: float = 0.9) -> np.ndarray:
-    """[H, W, 6] float32 rays (origin, unit direction) through pixel centres, built
-    like data_loader/colmap.py:10-20, 93-100 (pixel + 0.5, normalised)."""
-    pos = np.asarray(position, dtype=np.float64)
-    fwd = np.asarray(target, dtype=np.float64) - pos
-    fwd /= np.linalg.norm(fwd)
-    right = np.cross(fwd, np.asarray(up, dtype=np.float64))
-    right /= np.linalg.norm(right)
-    upv = np.cross(right, fwd)
-    f = 0.5 * height / math.tan(0.5 * fov)
-    xs = (np.arange(width, dtype=np.float64) + 0.5 - 0.5 * width) / f
-    ys = (np.arange(height, dtype=np.float64) + 0.5 - 0.5 * height) / f
-    gx, gy = np.meshgrid(xs, ys)
-    d = fwd[None, None, :] + gx[..., None] * right[None, None, :] - gy[..., None] * upv[None, None, :]
-    d /= np.linalg.norm(d, axis=-1, keepdims=True)
-    rays = np.empty((height, width, 6), dtype=np.float32)
-    rays[..., :3] = pos.astype(np.float32)
-    rays[..., 3:] = d.astype(np.float32)
-    return rays
+def pack_adjacency(adjacency: np.ndarray, offsets: np.ndarray) -> dict:
+    """CSR adjacency as arrays that compress well (rows are ascending and points Morton-ordered, so neighbour ids
+    sit near the row index): per-row first entry relative to the row, then in-row deltas; row lengths as bytes."""
+    counts = np.diff(offsets.astype(np.int64))
+    rows = np.repeat(np.arange(counts.shape[0], dtype=np.int64), counts)
+    a = adjacency.astype(np.int64)
+    delta = np.empty_like(a)
+    delta[1:] = a[1:] - a[:-1]
+    first = offsets[:-1].astype(np.int64)[counts > 0]
+    delta[first] = a[first] - rows[first]
+    if counts.max(initial=0) > 255 or np.abs(delta).max(initial=0) >= 2 ** 31:
+        raise RuntimeError("adjacency not packable")
+    return {"counts": counts.astype(np.uint8), "delta": delta.astype(np.int32)}
 
 
-def nearest_point(points: np.ndarray, query) -> int:
-    """Entry cell of a camera: brute-force nearest point (stands in for radfoam.nn,
-    src/aabb_tree/aabb_tree.cu:391-415, which is out of scope here)."""
-    q = np.asarray(query, dtype=np.float64)[None, :]
-    d2 = ((points.astype(np.float64) - q) ** 2).sum(axis=1)
-    return int(np.argmin(d2))
-
-
-def camera_dict(position, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), fov: float = 0.9,
-                width: int = 64, height: int = 48, model: str = "pinhole") -> dict:
-    """Camera in the dict form Pipeline.trace_benchmark takes
-    (torch_bindings/pipeline_bindings.cpp:526-547), numpy float32 vectors."""
-    pos = np.asarray(position, dtype=np.float64)
-    fwd = np.asarray(target, dtype=np.float64) - pos
-    fwd /= np.linalg.norm(fwd)
-    right = np.cross(fwd, np.asarray(up, dtype=np.float64))
-    right /= np.linalg.norm(right)
-    upv = np.cross(right, fwd)
-    return {
-        "position": pos.astype(np.float32), "forward": fwd.astype(np.float32),
-        "right": right.astype(np.float32), "up": upv.astype(np.float32),
-        "fov": float(fov), "width": int(width), "height": int(height), "model": model,
-    }
+def unpack_adjacency(counts: np.ndarray, delta: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    counts = counts.astype(np.int64)
+    offsets = np.zeros(counts.shape[0] + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    total = np.cumsum(delta.astype(np.int64))
+    nonempty = counts > 0
+    first = offsets[:-1][nonempty]
+    rows = np.arange(counts.shape[0], dtype=np.int64)[nonempty]
+    # within a row: value = row + (running sum - running sum before the row's first entry)
+    before = total[first] - delta.astype(np.int64)[first]
+    adjacency = total - np.repeat(before - rows, counts[nonempty])
+    return adjacency.astype(np.uint32), offsets.astype(np.uint32)
