@@ -51,8 +51,9 @@ def load_or_build_foam(num_points: int, log):
         log(f"foam cache hit: {path}")
         return f
     t0 = time.time()
-    adj_path = os.path.join(ROOT, "foam_cache", f"adjacency_{num_points}.npz")
-    if os.path.exists(adj_path):
+    adj_path = next((q for q in (os.path.join(ROOT, d, f"adjacency_{num_points}.npz")
+                                 for d in ("foam_cache", "foam_cache_big")) if os.path.exists(q)), None)
+    if adj_path:
         z = np.load(adj_path)
         f = foam.scene_foam(num_points, sh_degree=3, adjacency=foam.unpack_adjacency(z["counts"], z["delta"]))
         log(f"foam from the shipped adjacency: {f.num_points} points, E={f.adjacency.size}, {time.time() - t0:.1f} s")

@@ -175,3 +175,50 @@ def unpack_adjacency(counts: np.ndarray, delta: np.ndarray) -> tuple[np.ndarray,
     before = total[first] - delta.astype(np.int64)[first]
     adjacency = total - np.repeat(before - rows, counts[nonempty])
     return adjacency.astype(np.uint32), offsets.astype(np.uint32)
+
+
+def pinhole_rays(width: int, height: int, position, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0),
+                 fov: float = 0.9) -> np.ndarray:
+    """[H, W, 6] float32 rays (origin, unit direction) through pixel centres, built
+    like data_loader/colmap.py:10-20, 93-100 (pixel + 0.5, normalised)."""
+    pos = np.asarray(position, dtype=np.float64)
+    fwd = np.asarray(target, dtype=np.float64) - pos
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross(fwd, np.asarray(up, dtype=np.float64))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    f = 0.5 * height / math.tan(0.5 * fov)
+    xs = (np.arange(width, dtype=np.float64) + 0.5 - 0.5 * width) / f
+    ys = (np.arange(height, dtype=np.float64) + 0.5 - 0.5 * height) / f
+    gx, gy = np.meshgrid(xs, ys)
+    d = fwd[None, None, :] + gx[..., None] * right[None, None, :] - gy[..., None] * upv[None, None, :]
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rays = np.empty((height, width, 6), dtype=np.float32)
+    rays[..., :3] = pos.astype(np.float32)
+    rays[..., 3:] = d.astype(np.float32)
+    return rays
+
+
+def nearest_point(points: np.ndarray, query) -> int:
+    """Entry cell of a camera: brute-force nearest point (stands in for radfoam.nn,
+    src/aabb_tree/aabb_tree.cu:391-415, which is out of scope here)."""
+    q = np.asarray(query, dtype=np.float64)[None, :]
+    d2 = ((points.astype(np.float64) - q) ** 2).sum(axis=1)
+    return int(np.argmin(d2))
+
+
+def camera_dict(position, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), fov: float = 0.9,
+                width: int = 64, height: int = 48, model: str = "pinhole") -> dict:
+    """Camera in the dict form Pipeline.trace_benchmark takes
+    (torch_bindings/pipeline_bindings.cpp:526-547), numpy float32 vectors."""
+    pos = np.asarray(position, dtype=np.float64)
+    fwd = np.asarray(target, dtype=np.float64) - pos
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross(fwd, np.asarray(up, dtype=np.float64))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    return {
+        "position": pos.astype(np.float32), "forward": fwd.astype(np.float32),
+        "right": right.astype(np.float32), "up": upv.astype(np.float32),
+        "fov": float(fov), "width": int(width), "height": int(height), "model": model,
+    }
