@@ -2,7 +2,7 @@
 # Round 2, call 6 (8 GPUs): the N = 8 bench with the fused peer-memory exchange kernel, and with NCCL for comparison.
 mkdir -p gpurun_out
 run() { tag=$1; n=$2; shift 2; env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus $n --steps 20 --warmup 5 --no-cpu-baseline 2> gpurun_out/r2c6_bench_$tag.err | grep '^{' > gpurun_out/r2c6_bench_$tag.json; }
+    bench.py --gpus $n --steps 12 --warmup 4 --no-cpu-baseline 2> gpurun_out/r2c6_bench_$tag.err | grep '^{' > gpurun_out/r2c6_bench_$tag.json; }
 run n8_fused 8 RFB_FUSED_REDUCE=1
 run n8_nccl 8 RFB_FUSED_REDUCE=0
 run n4_fused 4 RFB_FUSED_REDUCE=1
