@@ -447,7 +447,8 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     launches = rp.launch_count()
     # per-phase durations from a separate short pass (events between the phases would serialise the timed loop)
-    phase_rows = []
+    phase_rows, exchange_rows = [], []
+    tracer.profile_reduce = True
     for _ in range(3):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         pipe.invalidate_cache()
@@ -466,9 +467,23 @@ def run_ours(args):
             bwd_ms.append(kb)
         phase_rows.append([ev[0].elapsed_time(ev[1]) - kf, kf, ev[1].elapsed_time(ev[2]) - kb, kb,
                            ev[2].elapsed_time(ev[3])])
+        if tracer.last_reduce_ms():
+            exchange_rows.append(tracer.last_reduce_ms())
+    tracer.profile_reduce = False
     phase_names_dev = ("relayout_and_tape_setup", "forward_kernel", "accumulator_zero_fill", "backward_kernel",
                        "grad_reduce_and_finalize")
     phases_ms = {n: round(float(np.median([r[j] for r in phase_rows])), 4) for j, n in enumerate(phase_names_dev)}
+    if exchange_rows:
+        phases_ms["grad_reduce_and_finalize_parts"] = {k: round(float(np.median([r[k] for r in exchange_rows])), 4)
+                                                       for k in exchange_rows[0]}
+    if world > 1:  # every rank's phases: the step is as long as its slowest rank
+        import torch.distributed as dist
+
+        mine = torch.tensor([[r[j] for j in range(5)] for r in phase_rows], dtype=torch.float64, device=dev).median(0).values
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        table = torch.stack(every).cpu().numpy()
+        phases_ms["per_rank"] = {n: [round(float(x), 3) for x in table[:, j]] for j, n in enumerate(phase_names_dev)}
     pipe.set_profiling(False)
     ms_per_step = total_ms / args.steps
 

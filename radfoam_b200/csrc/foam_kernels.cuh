@@ -1034,6 +1034,8 @@ struct PeerReduceParams {
     float *points_grad[kMaxPeers];
     uint32_t world, num_points, first_block, block_stride;
     int scrub;
+    uint32_t rank;
+    int debug_mode; // measurement only (RFB_PEER_DEBUG): 1 = store to the own rank only, 2 = load the own accumulator only
 };
 
 // WORLD > 0: the number of ranks as a compile-time constant (2, 4, 8: exactly that many loads per thread in
@@ -1061,7 +1063,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
 #pragma unroll
             for (int w = 0; w < SLOTS; ++w)
                 if (w < world)
-                    v[w] = *reinterpret_cast<const float4 *>(p.acc[w] + off);
+                    v[w] = *reinterpret_cast<const float4 *>(p.acc[p.debug_mode == 2 ? p.rank : w] + off);
             float4 s = v[0];
 #pragma unroll
             for (int w = 1; w < SLOTS; ++w)
@@ -1091,7 +1093,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
             }
             const uint64_t e0 = (uint64_t)row0 * A + 4ull * t;
             for (uint32_t w = 0; w < p.world; ++w) {
-                AttrT *dst = reinterpret_cast<AttrT *>(p.attr_grad[w]) + e0;
+                AttrT *dst = reinterpret_cast<AttrT *>(p.attr_grad[p.debug_mode == 1 ? p.rank : w]) + e0;
                 if (full) {
                     if (sizeof(AttrT) == 4)
                         *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
@@ -1119,7 +1121,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
             }
             const uint64_t e0 = (uint64_t)row0 * 3 + 4ull * u;
             for (uint32_t w = 0; w < p.world; ++w) {
-                float *dst = p.points_grad[w] + e0;
+                float *dst = p.points_grad[p.debug_mode == 1 ? p.rank : w] + e0;
                 if (full) {
                     *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
                 } else {

@@ -979,6 +979,9 @@ int rfb_reduce_finalize_peers(rfb_pipeline *p, uint32_t world, uint32_t rank, ui
     pr.first_block = rank;
     pr.block_stride = world;
     pr.scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
+    pr.rank = rank;
+    const char *dbg = getenv("RFB_PEER_DEBUG");
+    pr.debug_mode = dbg ? atoi(dbg) : 0;
     const uint32_t mine = (num_blocks + world - 1 - rank) / world;
     if (mine == 0)
         return 0;

@@ -91,6 +91,8 @@ class ShardedTracer:
             fused_reduce = os.environ.get("RFB_FUSED_REDUCE", "1") != "0"
         self.fused_reduce = fused_reduce
         self._peer = None          # set-up state of the fused path; False = tried and unavailable
+        self.profile_reduce = False  # record CUDA events around the parts of the fused exchange (bench.py)
+        self.last_reduce_events = None
         self.fused_reduce_error = None
 
     # -- partition helpers bound to this rank
@@ -119,6 +121,16 @@ class ShardedTracer:
         if self._peer:
             return "one fused peer-memory reduce+finalize kernel per rank (NVLink, symmetric memory)"
         return "one NCCL all-reduce"
+
+    def last_reduce_ms(self):
+        """Durations of the last fused exchange on this rank (after a synchronize): wait for the slowest rank's
+        backward (barrier), the peer kernel, the closing barrier, the copies out of symmetric memory."""
+        ev = self.last_reduce_events
+        if not ev:
+            return None
+        names = ("barrier_all_accumulators_complete", "peer_reduce_finalize_kernel", "barrier_all_stores_landed",
+                 "copy_out_of_symmetric_memory")
+        return {n: round(float(ev[i].elapsed_time(ev[i + 1])), 4) for i, n in enumerate(names)}
 
     def _peer_setup(self, num_points: int, device):
         """Symmetric buffers [accumulator | attr_grad | points_grad] + peer pointer tables, once per size."""
@@ -176,11 +188,21 @@ class ShardedTracer:
             return pipe.trace_backward_finalize(num_points, device, scrub_nonfinite=scrub_nonfinite)
         st = self._peer
         if st:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.profile_reduce else None
+            mark = (lambda i: ev[i].record()) if ev else (lambda i: None)
+            mark(0)
             st["hdl"].barrier(channel=0)   # every rank's accumulator is complete
+            mark(1)
             pipe.reduce_finalize_peers(self.world, self.rank, num_points, st["peer_acc"], st["peer_attr"],
                                        st["peer_pts"], device, scrub_nonfinite=scrub_nonfinite)
+            mark(2)
             st["hdl"].barrier(channel=1)   # every rank's stores have landed; accumulators may be reused
-            return st["pts"].clone(), st["attr"].clone()
+            mark(3)
+            out = st["pts"].clone(), st["attr"].clone()
+            mark(4)
+            if ev:
+                self.last_reduce_events = ev
+            return out
         dist.all_reduce(acc if acc is not None else pipe.grad_accumulator(device), op=dist.ReduceOp.SUM,
                         group=self.group)
         return pipe.trace_backward_finalize(num_points, device, scrub_nonfinite=scrub_nonfinite)
