@@ -247,12 +247,25 @@ int rfb_trace_backward_finalize_params(rfb_pipeline *pipeline, uint32_t num_poin
  * peer_attribute_grad[w] ([N][A], attr dtype) and peer_points_grad[w] ([N][3] f32).  After ALL ranks have run
  * it every rank holds the complete gradients, bit-identical across ranks.  The CALLER provides the two
  * cross-GPU barriers: every rank's accumulate must have finished before any rank starts, and every rank must
- * have finished before the outputs are read or an accumulator is written again. */
+ * have finished before the outputs are read or an accumulator is written again.
+ *
+ * `multicast` (optional, NULL = none): NVSwitch multicast addresses of the same three arrays (one mapping that
+ * reaches every rank's copy; e.g. torch symmetric memory's multicast_ptr + the array's offset).  With it a rank
+ * reads its share with multimem.ld_reduce -- the switch returns the sum over all ranks -- and writes it with
+ * multimem.st -- the switch replicates it --, so only 1/world of the arrays crosses each GPU's link in each
+ * direction instead of (world-1)/world.  The sum is then formed by the switch (order unspecified, fp32);
+ * every rank still receives identical bits. */
+typedef struct rfb_multicast {
+    const float *acc;
+    void *attribute_grad;
+    float *points_grad;
+} rfb_multicast;
 int rfb_set_grad_accumulator(rfb_pipeline *pipeline, float *ptr, uint64_t num_floats);
 int rfb_reduce_finalize_peers(rfb_pipeline *pipeline, uint32_t world, uint32_t rank,
                               uint32_t num_points, const float *const *peer_acc,
                               void *const *peer_attribute_grad,
-                              float *const *peer_points_grad, uint32_t flags,
+                              float *const *peer_points_grad,
+                              const rfb_multicast *multicast, uint32_t flags,
                               void *stream);
 
 /* forward-only render with in-kernel ray generation (camera.h:56-85) and RGBA8

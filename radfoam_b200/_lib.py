@@ -32,6 +32,10 @@ class SceneParams(ctypes.Structure):  # rfb_scene_params
     _fields_ = [("att_dc", c_void_p), ("att_sh", c_void_p), ("density", c_void_p), ("activation_scale", c_float)]
 
 
+class Multicast(ctypes.Structure):  # rfb_multicast
+    _fields_ = [("acc", c_void_p), ("attribute_grad", c_void_p), ("points_grad", c_void_p)]
+
+
 class LaunchOpts(ctypes.Structure):  # rfb_launch_opts
     _fields_ = [("scene_version", c_uint64), ("image_width", c_uint32), ("flags", c_uint32)]
 
@@ -69,7 +73,7 @@ SIGNATURES = {
     "rfb_trace_backward_finalize_params": (c_int, [_P, c_uint32, _P, _P, _P, _P, c_uint32, _P]),
     "rfb_set_grad_accumulator": (c_int, [_P, _P, c_uint64]),
     "rfb_reduce_finalize_peers": (c_int, [_P, c_uint32, c_uint32, c_uint32, POINTER(_P), POINTER(_P), POINTER(_P),
-                                          c_uint32, _P]),
+                                          POINTER(Multicast), c_uint32, _P]),
     "rfb_trace_benchmark": (c_int, [_P, POINTER(TraceSettings), c_uint32, _P, _P, _P, _P, _P,
                                     POINTER(Camera), _P, _P, POINTER(LaunchOpts), _P]),
     "rfb_launch_count": (c_uint64, []),

@@ -67,6 +67,38 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 #endif
 }
 
+// NVSwitch multicast (NVLS): one load returns the SUM of the word at the same offset of every GPU's copy -- the
+// switch does the reduction --, one store writes all copies.  `p` is an address in the multicast mapping of a
+// symmetric allocation.
+__device__ __forceinline__ float4 multimem_ld_reduce_add_v4(const float *p) {
+#ifdef RFB_EMU
+    return rfb_emu_multimem_ld_reduce_v4(p);
+#else
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void multimem_st_v4(float *p, float4 v) {
+#ifdef RFB_EMU
+    rfb_emu_multimem_st(p, &v, 16);
+#else
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void multimem_st_v2(void *p, float2 v) {
+#ifdef RFB_EMU
+    rfb_emu_multimem_st(p, &v, 8);
+#else
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------- SH basis
 // Real SH basis of the (unit) direction; same formulas and evaluation order as
 // sh_coefficients<deg>() (sh_utils.cuh:34-70) so nvcc contracts them alike.

@@ -1036,6 +1036,12 @@ struct PeerReduceParams {
     int scrub;
     uint32_t rank;
     int debug_mode; // measurement only (RFB_PEER_DEBUG): 1 = store to the own rank only, 2 = load the own accumulator only
+    // NVSwitch multicast addresses of the same three arrays (all null: plain peer loads / stores).  With them a
+    // rank pulls only its own share through its link (the switch sums the W copies) and pushes it once (the
+    // switch replicates it): (W-1)/W of the NVLink traffic of the peer-pointer form disappears.
+    const float *mc_acc;
+    void *mc_attr_grad;
+    float *mc_points_grad;
 };
 
 // WORLD > 0: the number of ranks as a compile-time constant (2, 4, 8: exactly that many loads per thread in
@@ -1057,6 +1063,9 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
         const uint32_t nrows = min((uint32_t)kPeerRows, p.num_points - row0);
         if (t < nrows * ROW_VECS) {
             const uint64_t off = (uint64_t)row0 * GR + 4ull * t;
+            if (p.mc_acc) {
+                *reinterpret_cast<float4 *>(rows + 4 * t) = multimem_ld_reduce_add_v4(p.mc_acc + off);
+            } else {
             constexpr int SLOTS = WORLD > 0 ? WORLD : kMaxPeers;
             const int world = WORLD > 0 ? WORLD : (int)p.world;
             float4 v[SLOTS];
@@ -1074,9 +1083,11 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
                     s.w += v[w].w;
                 }
             *reinterpret_cast<float4 *>(rows + 4 * t) = s;
+            }
         }
         __syncthreads();
         const bool full = nrows == kPeerRows;
+        const bool multicast = p.mc_acc != nullptr && full; // the ragged last block goes peer by peer
         if (t < ATTR_VECS) {
             // four consecutive elements of the block's [rows][A] output
             AttrT o[4];
@@ -1092,6 +1103,13 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
                 o[k] = a;
             }
             const uint64_t e0 = (uint64_t)row0 * A + 4ull * t;
+            if (multicast) {
+                AttrT *dst = reinterpret_cast<AttrT *>(p.mc_attr_grad) + e0;
+                if (sizeof(AttrT) == 4)
+                    multimem_st_v4(reinterpret_cast<float *>(dst), *reinterpret_cast<const float4 *>(o));
+                else
+                    multimem_st_v2(dst, *reinterpret_cast<const float2 *>(o));
+            } else
             for (uint32_t w = 0; w < p.world; ++w) {
                 AttrT *dst = reinterpret_cast<AttrT *>(p.attr_grad[p.debug_mode == 1 ? p.rank : w]) + e0;
                 if (full) {
@@ -1120,6 +1138,9 @@ __global__ void __launch_bounds__(256) reduce_finalize_peers_kernel(const PeerRe
                 o[k] = x;
             }
             const uint64_t e0 = (uint64_t)row0 * 3 + 4ull * u;
+            if (multicast)
+                multimem_st_v4(p.mc_points_grad + e0, *reinterpret_cast<const float4 *>(o));
+            else
             for (uint32_t w = 0; w < p.world; ++w) {
                 float *dst = p.points_grad[p.debug_mode == 1 ? p.rank : w] + e0;
                 if (full) {

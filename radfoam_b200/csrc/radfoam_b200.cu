@@ -953,9 +953,15 @@ int rfb_set_grad_accumulator(rfb_pipeline *p, float *ptr, uint64_t num_floats) {
 
 int rfb_reduce_finalize_peers(rfb_pipeline *p, uint32_t world, uint32_t rank, uint32_t num_points,
                               const float *const *peer_acc, void *const *peer_attribute_grad,
-                              float *const *peer_points_grad, uint32_t flags, void *stream_) {
+                              float *const *peer_points_grad, const rfb_multicast *multicast, uint32_t flags,
+                              void *stream_) {
     if (!p || !peer_acc || !peer_attribute_grad || !peer_points_grad)
         return fail("rfb_reduce_finalize_peers: NULL argument");
+    if (multicast && (!multicast->acc || !multicast->attribute_grad || !multicast->points_grad))
+        return fail("rfb_reduce_finalize_peers: incomplete multicast addresses");
+    if (multicast && ((reinterpret_cast<uintptr_t>(multicast->acc) | reinterpret_cast<uintptr_t>(multicast->attribute_grad) |
+                       reinterpret_cast<uintptr_t>(multicast->points_grad)) & 15u))
+        return fail("rfb_reduce_finalize_peers: multicast addresses must be 16-byte aligned");
     if (world == 0 || world > (uint32_t)kMaxPeers || rank >= world)
         return fail("rfb_reduce_finalize_peers: world must be 1.." + std::to_string(kMaxPeers) + " and rank < world");
     if (num_points == 0)
@@ -982,6 +988,9 @@ int rfb_reduce_finalize_peers(rfb_pipeline *p, uint32_t world, uint32_t rank, ui
     pr.rank = rank;
     const char *dbg = getenv("RFB_PEER_DEBUG");
     pr.debug_mode = dbg ? atoi(dbg) : 0;
+    pr.mc_acc = multicast ? multicast->acc : nullptr;
+    pr.mc_attr_grad = multicast ? multicast->attribute_grad : nullptr;
+    pr.mc_points_grad = multicast ? multicast->points_grad : nullptr;
     const uint32_t mine = (num_blocks + world - 1 - rank) / world;
     if (mine == 0)
         return 0;

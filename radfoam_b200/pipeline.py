@@ -584,13 +584,17 @@ class Pipeline:
         _lib.check(self._lib.rfb_set_grad_accumulator(self._handle, acc.data_ptr(), acc.numel()))
 
     def reduce_finalize_peers(self, world, rank, num_points, peer_acc, peer_attr_grad, peer_points_grad, device,
-                              scrub_nonfinite=False):
+                              scrub_nonfinite=False, multicast=None):
         """``rfb_reduce_finalize_peers``: the pointer tables are ctypes ``c_void_p`` arrays of ``world`` device
-        addresses valid on this device.  The caller provides the cross-GPU barriers around it."""
+        addresses valid on this device; ``multicast`` = optional ``(acc, attr_grad, points_grad)`` NVSwitch
+        multicast addresses.  The caller provides the cross-GPU barriers around it."""
+        mc = None
+        if multicast is not None:
+            mc = ctypes.byref(_lib.Multicast(*[int(a) for a in multicast]))
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(self._lib.rfb_reduce_finalize_peers(
-                self._handle, world, rank, num_points, peer_acc, peer_attr_grad, peer_points_grad,
+                self._handle, world, rank, num_points, peer_acc, peer_attr_grad, peer_points_grad, mc,
                 _lib.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, stream))
 
     def trace_backward_finalize(self, num_points, device, scrub_nonfinite=False):

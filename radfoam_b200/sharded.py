@@ -118,6 +118,9 @@ class ShardedTracer:
     def reduction_name(self) -> str:
         if self.world == 1:
             return "no collective"
+        if self._peer and self._peer["multicast"]:
+            return ("one fused reduce+finalize kernel per rank over NVSwitch multicast (multimem.ld_reduce / "
+                    "multimem.st on symmetric memory)")
         if self._peer:
             return "one fused peer-memory reduce+finalize kernel per rank (NVLink, symmetric memory)"
         return "one NCCL all-reduce"
@@ -163,7 +166,12 @@ class ShardedTracer:
             arr = lambda off: (ctypes.c_void_p * self.world)(*[b + 4 * off for b in bases])  # noqa: E731
             attr_view = buf[acc_f:acc_f + attr_f]
             attr_view = (attr_view.view(torch.float16) if half else attr_view)[:num_points * adim].view(num_points, adim)
-            st = dict(num_points=num_points, buf=buf, hdl=hdl, acc=buf[:acc_f].view(num_points, gr),
+            mc_base = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            multicast = None
+            if mc_base and os.environ.get("RFB_MULTICAST", "1") != "0":  # NVSwitch multicast (NVLS) is available
+                multicast = (mc_base, mc_base + 4 * acc_f, mc_base + 4 * (acc_f + attr_f))
+            st = dict(num_points=num_points, buf=buf, hdl=hdl, multicast=multicast,
+                      acc=buf[:acc_f].view(num_points, gr),
                       attr=attr_view, pts=buf[acc_f + attr_f:acc_f + attr_f + num_points * 3].view(num_points, 3),
                       peer_acc=arr(0), peer_attr=arr(acc_f), peer_pts=arr(acc_f + attr_f))
         except Exception as e:  # noqa: BLE001
@@ -194,7 +202,8 @@ class ShardedTracer:
             st["hdl"].barrier(channel=0)   # every rank's accumulator is complete
             mark(1)
             pipe.reduce_finalize_peers(self.world, self.rank, num_points, st["peer_acc"], st["peer_attr"],
-                                       st["peer_pts"], device, scrub_nonfinite=scrub_nonfinite)
+                                       st["peer_pts"], device, scrub_nonfinite=scrub_nonfinite,
+                                       multicast=st["multicast"])
             mark(2)
             st["hdl"].barrier(channel=1)   # every rank's stores have landed; accumulators may be reused
             mark(3)

@@ -392,6 +392,49 @@ inline unsigned atomicMax(unsigned *p, unsigned v) {
     return old;
 }
 inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+// NVSwitch multicast stand-in: one registered group = `world` equally sized buffers reachable through a fake base
+// address; ld_reduce sums the copies in rank order (the switch's order is unspecified), st writes every copy.
+namespace emu {
+struct MulticastGroup {
+    char *fake = nullptr;
+    size_t bytes = 0;
+    std::vector<char *> copies;
+};
+inline MulticastGroup &multicast() {
+    static MulticastGroup g;
+    return g;
+}
+inline size_t multicast_offset(const void *p) {
+    auto &g = multicast();
+    const char *c = reinterpret_cast<const char *>(p);
+    if (!g.fake || c < g.fake || c >= g.fake + g.bytes)
+        std::abort();
+    return (size_t)(c - g.fake);
+}
+} // namespace emu
+inline float4 rfb_emu_multimem_ld_reduce_v4(const float *p) {
+    const size_t off = emu::multicast_offset(p);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool first = true;
+    for (char *c : emu::multicast().copies) {
+        const float4 v = *reinterpret_cast<const float4 *>(c + off);
+        if (first) {
+            s = v;
+            first = false;
+        } else {
+            s.x += v.x;
+            s.y += v.y;
+            s.z += v.z;
+            s.w += v.w;
+        }
+    }
+    return s;
+}
+inline void rfb_emu_multimem_st(void *p, const void *value, size_t n) {
+    const size_t off = emu::multicast_offset(p);
+    for (char *c : emu::multicast().copies)
+        std::memcpy(c + off, value, n);
+}
 inline void rfb_emu_red_add_v4(float *p, float a, float b, float c, float d) {
     emu::counters.red_v4.fetch_add(1, std::memory_order_relaxed);
     atomicAdd(p, a);

@@ -173,18 +173,39 @@ class EmuPipeline:
             product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
         return out
 
-    def reduce_finalize_peers(self, rank, accumulators, scrub_nonfinite=False):
+    def reduce_finalize_peers(self, rank, accumulators, scrub_nonfinite=False, multicast=False):
         """rfb_reduce_finalize_peers with `accumulators` (one [N, grad_row] float32 array per rank) standing in for
         the peer-mapped buffers; returns THIS rank's writes into every rank's outputs as (attr_grads, points_grads),
-        lists of arrays pre-filled with a sentinel so that the rows a rank does not own are recognisable."""
+        lists of arrays pre-filled with a sentinel so that the rows a rank does not own are recognisable.
+        `multicast`: go through the emulated NVSwitch multicast group instead of the peer pointers."""
         world, n = len(accumulators), accumulators[0].shape[0]
-        accs = [_c(a, np.float32) for a in accumulators]
-        attr = [np.full((n, self.attr_dim), 7.0, self.dtype) for _ in range(world)]
-        pts = [np.full((n, 3), 7.0, np.float32) for _ in range(world)]
+        gr = accumulators[0].shape[1]
+        itemsize = np.dtype(self.dtype).itemsize
+        acc_b, attr_b, pts_b = n * gr * 4, (n * self.attr_dim * itemsize + 15) // 16 * 16, (n * 3 * 4 + 15) // 16 * 16
+        # one allocation per rank laid out like radfoam_b200/sharded.py's symmetric buffer: [acc | attr | pts]
+        bufs = [np.zeros(acc_b + attr_b + pts_b, np.uint8) for _ in range(world)]
+        accs, attr, pts = [], [], []
+        for w in range(world):
+            a = bufs[w][:acc_b].view(np.float32).reshape(n, gr)
+            a[...] = accumulators[w]
+            accs.append(a)
+            t = bufs[w][acc_b:acc_b + n * self.attr_dim * itemsize].view(self.dtype).reshape(n, self.attr_dim)
+            t[...] = 7.0
+            attr.append(t)
+            q = bufs[w][acc_b + attr_b:acc_b + attr_b + n * 12].view(np.float32).reshape(n, 3)
+            q[...] = 7.0
+            pts.append(q)
         table = lambda arrs: (ctypes.c_void_p * world)(*[a.ctypes.data for a in arrs])  # noqa: E731
+        mc = None
+        if multicast:
+            self.lib.rfe_set_multicast.restype = ctypes.c_void_p
+            self.lib.rfe_set_multicast.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.c_uint64]
+            base = self.lib.rfe_set_multicast(table(bufs), world, acc_b + attr_b + pts_b)
+            mc = ctypes.byref(product_abi.Multicast(base, base + acc_b, base + acc_b + attr_b))
         _check(self.lib.rfb_reduce_finalize_peers(
-            self.handle, world, rank, n, table(accs), table(attr), table(pts),
+            self.handle, world, rank, n, table(accs), table(attr), table(pts), mc,
             product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
+        self._keep_peers = bufs
         return attr, pts
 
     def trace_benchmark(self, points, attributes, adjacency, offsets, adjacent_diff, camera, start_point,

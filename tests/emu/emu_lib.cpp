@@ -53,3 +53,21 @@ extern "C" void rfe_counters(uint64_t *red_v4, uint64_t *red_v2, uint64_t *colle
         emu::counters.collectives = 0;
     }
 }
+
+// NVSwitch multicast stand-in for tests: `world` buffers of `bytes` each; returns the fake base address to pass as the
+// multicast pointer (world == 0 clears the group).
+extern "C" void *rfe_set_multicast(void *const *copies, uint32_t world, uint64_t bytes) {
+    auto &g = emu::multicast();
+    static std::vector<char> fake_space;
+    g.copies.clear();
+    g.fake = nullptr;
+    g.bytes = 0;
+    if (world == 0)
+        return nullptr;
+    fake_space.assign(bytes + 64, 0); // only its address range is used
+    g.fake = fake_space.data();
+    g.bytes = bytes;
+    for (uint32_t w = 0; w < world; ++w)
+        g.copies.push_back(reinterpret_cast<char *>(copies[w]));
+    return g.fake;
+}

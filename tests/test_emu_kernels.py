@@ -296,10 +296,11 @@ print("ok")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("multicast", [False, True], ids=["peer_pointers", "nvswitch_multicast"])
 @pytest.mark.parametrize("world,num_points,deg,dtype", [(2, 64, 3, np.float32), (3, 45, 3, np.float32),
                                                         (8, 150, 3, np.float32), (2, 37, 1, np.float16),
                                                         (4, 16, 0, np.float32), (5, 3, 2, np.float16)])
-def test_fused_peer_reduce_finalize(world, num_points, deg, dtype):
+def test_fused_peer_reduce_finalize(world, num_points, deg, dtype, multicast):
     """The multi-GPU exchange kernel (rfb_reduce_finalize_peers) on the CPU: every rank sums its row blocks over all
     ranks' accumulators in rank order, finalizes, and writes them into every rank's outputs; after all ranks ran,
     every rank holds exactly what all-reduce + finalize gives (ragged last block, fp16 outputs, scrub)."""
@@ -321,7 +322,7 @@ def test_fused_peer_reduce_finalize(world, num_points, deg, dtype):
     got_pts = [np.full((num_points, 3), 7.0, np.float32) for _ in range(world)]
     written = np.zeros(num_points, dtype=np.int64)
     for rank in range(world):
-        attr, pts = pipe.reduce_finalize_peers(rank, accs, scrub_nonfinite=True)
+        attr, pts = pipe.reduce_finalize_peers(rank, accs, scrub_nonfinite=True, multicast=multicast)
         mine = (np.arange(num_points) // 16) % world == rank      # blocks of 16 rows, round-robin
         for w in range(world):
             assert np.all(attr[w][~mine] == 7.0) and np.all(pts[w][~mine] == 7.0)   # nothing outside its share

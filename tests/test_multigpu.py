@@ -20,7 +20,9 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, fused, results):
+def _worker(rank, world, port, mode, results):
+    fused = mode != "nccl_all_reduce"
+    os.environ["RFB_MULTICAST"] = "1" if mode == "fused_nvswitch_multicast" else "0"
     import torch
     import torch.distributed as dist
 
@@ -56,6 +58,7 @@ def _worker(rank, world, port, fused, results):
         if rank == 0:
             results["same_on_all_ranks"] = bool(all(torch.equal(all_bits[0], b) for b in all_bits))
             results["fused_active"] = bool(tracer._peer)
+            results["multicast_active"] = bool(tracer._peer and tracer._peer["multicast"])
             results["fused_error"] = tracer.fused_reduce_error
             single = radfoam_b200.create_pipeline(3)
             sf = single.trace_forward(*scene, full["rays"], full["start"], depth_quantiles=full["dq"])
@@ -71,8 +74,9 @@ def _worker(rank, world, port, fused, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused_peer_kernel", "nccl_all_reduce"])
-def test_two_gpu_sharded_matches_single_gpu(fused):
+@pytest.mark.parametrize("mode", ["fused_nvswitch_multicast", "fused_peer_pointers", "nccl_all_reduce"])
+def test_two_gpu_sharded_matches_single_gpu(mode):
+    fused = mode != "nccl_all_reduce"
     import torch
     import torch.multiprocessing as mp
 
@@ -81,9 +85,12 @@ def test_two_gpu_sharded_matches_single_gpu(fused):
     world = 2
     with mp.Manager() as manager:
         results = manager.dict()
-        mp.spawn(_worker, args=(world, _free_port(), fused, results), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), mode, results), nprocs=world, join=True)
         results = dict(results)
-    print("fused path active:", results["fused_active"], results["fused_error"])
+    print("fused path active:", results["fused_active"], "multicast:", results["multicast_active"],
+          results["fused_error"])
+    if mode == "fused_peer_pointers":
+        assert not results["multicast_active"]
     assert results["fused_active"] == fused or (fused and results["fused_error"])  # falls back only with a reason
     assert results["same_on_all_ranks"]
     assert results["rgba_equal"] and results["nint_equal"]     # same per-ray code: bit-identical
