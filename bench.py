@@ -84,7 +84,10 @@ def pack_foam_adjacency(num_points: int):
 
 def workload_name(f, width: int, height: int) -> str:
     """Identical in both arms (the driver compares the strings)."""
-    return (f"config4: synthetic foam {f.num_points} points (E={f.adjacency.size}), {width}x{height} frame, "
+    name = {(1_048_576, 1920, 1080): "config4", (2_097_152, 1920, 1080): "config3-sized",
+            (4_194_304, 3840, 2160): "config5-sized", (524_288, 1920, 1080): "config2-sized"}.get(
+        (f.num_points, width, height), "custom")
+    return (f"{name}: synthetic foam {f.num_points} points (E={f.adjacency.size}), {width}x{height} frame, "
             "Q=2, sh_degree 3, fwd+bwd")
 
 
