@@ -168,7 +168,11 @@ class ShardedTracer:
             attr_view = (attr_view.view(torch.float16) if half else attr_view)[:num_points * adim].view(num_points, adim)
             mc_base = int(getattr(hdl, "multicast_ptr", 0) or 0)
             multicast = None
-            if mc_base and os.environ.get("RFB_MULTICAST", "1") != "0":  # NVSwitch multicast (NVLS) is available
+            # NVSwitch multicast (NVLS) when available -- from 8 ranks on: per GPU and direction it moves
+            # (1 + 1/W) accumulator sizes instead of 2 (W-1)/W, at ~25 % less throughput per byte.  Measured at
+            # 1 M points: W = 2 peers 0.33 / multicast 0.57 ms, W = 8 peers 0.58 / multicast 0.47 ms.
+            want = os.environ.get("RFB_MULTICAST")
+            if mc_base and (want == "1" or (want is None and self.world >= 8)):
                 multicast = (mc_base, mc_base + 4 * acc_f, mc_base + 4 * (acc_f + attr_f))
             st = dict(num_points=num_points, buf=buf, hdl=hdl, multicast=multicast,
                       acc=buf[:acc_f].view(num_points, gr),
