@@ -81,6 +81,35 @@ class FoamScene:
         return TraceRays.apply(pipeline, points, attributes, adjacency, offsets, rays, start_point, depth_quantiles,
                                return_contribution)
 
+    # ------------------------------------------------------------------ scene.py:497-548
+    def collect_error_map(self, pipeline, rays, rgbs, white_bkg=True, downsample=2, generator=None, fused=True):
+        """The densification pass's error map (``RadFoamScene.collect_error_map``): for every view ``rays[v]``
+        (``[V, H, W, 6]``, targets ``rgbs[V, H, W, 3]``) a randomly offset ``downsample``-strided sub-image is rendered
+        with the contribution output, the L1 colour loss is back-propagated, and per point the gradient norm of its
+        position is accumulated and the contribution maximised.  Returns ``(point_error [N,1], point_contribution [N,1])``.
+        The scene's tensors must require grad; their ``.grad`` is cleared per view like ``zero_grad(set_to_none=True)``."""
+        from . import pipeline as _p
+
+        points = self.primal_points
+        start_points = _p.starting_points(rays[:, 0, 0].to(points.device), points)
+        point_error = torch.zeros_like(points[..., 0:1]).detach()
+        point_contribution = torch.zeros_like(points[..., 0:1]).detach()
+        params = [points, self.att_dc, self.att_sh, self.density]
+        for v in range(rays.shape[0]):
+            d = torch.randint(0, downsample, (2,), generator=generator)
+            ray_batch = rays[v:v + 1, int(d[0])::downsample, int(d[1])::downsample, :].to(points.device)
+            rgb_batch = rgbs[v:v + 1, int(d[0])::downsample, int(d[1])::downsample, :].to(points.device)
+            rgba, _, contribution, _, _ = self.forward(pipeline, ray_batch, start_points[v], return_contribution=True,
+                                                       fused=fused)
+            opacity = rgba[..., -1:]
+            rgb = rgba[..., :3] + (1 - opacity) if white_bkg else rgba[..., :3]
+            (rgb_batch - rgb).abs().mean(dim=-1).sum().backward()
+            point_error += points.grad.norm(dim=-1, keepdim=True).detach()
+            point_contribution = torch.maximum(point_contribution, contribution.detach().to(point_contribution.dtype))
+            for t in params:
+                t.grad = None
+        return point_error, point_contribution
+
     @property
     def num_points(self) -> int:
         return int(self.primal_points.shape[0])

@@ -256,3 +256,48 @@ def test_training_step_is_cuda_graph_capturable(torch_cuda):
     assert torch.equal(got[0], want[0])
     for a, b in zip(got[1:], want[1:]):
         assert float((a - b).abs().max() / b.abs().max()) <= 1e-5
+
+
+def test_collect_error_map_matches_the_reference_loop(torch_cuda):
+    """the densification pass's error map (scene.py:497-548) through FoamScene.collect_error_map
+    (parameter-form scene, device-side start points) against the same loop spelled out with the reference's own
+    autograd op on the reference's own kernels."""
+    import radfoam_b200
+    from radfoam_b200 import foam, scene_io
+
+    torch = torch_cuda
+    mod = load_reference_op()
+    f = common.scene_case(20000, 160, 96, q=2).foam
+    views, height, width = 3, 48, 80
+    cams = [(2.5, 2.5, 2.5), (-2.5, 2.0, 1.5), (0.5, -3.0, 2.0)]
+    rays = torch.from_numpy(np.stack([foam.pinhole_rays(width, height, c, fov=0.9) for c in cams]))
+    rgbs = torch.rand((views, height, width, 3), generator=torch.Generator().manual_seed(5))
+    scene = scene_io.FoamScene.from_foam(f, device="cuda")
+    for t in (scene.primal_points, scene.att_dc, scene.att_sh, scene.density):
+        t.requires_grad_(True)
+    pipe = radfoam_b200.create_pipeline(3, "float32")
+    err, contrib = scene.collect_error_map(pipe, rays, rgbs, generator=torch.Generator().manual_seed(9))
+
+    # the reference's loop: get_trace_data with torch ops, TraceRays from the reference's file, its own kernels
+    ref_pipe = ReferencePipeline()
+    gen = torch.Generator().manual_seed(9)
+    want_err = torch.zeros_like(err)
+    want_contrib = torch.zeros_like(contrib)
+    starts = [int(foam.nearest_point(f.points, c)) for c in cams]
+    for v in range(views):
+        d = torch.randint(0, 2, (2,), generator=gen)
+        ray_batch = rays[v:v + 1, int(d[0])::2, int(d[1])::2, :].cuda()
+        rgb_batch = rgbs[v:v + 1, int(d[0])::2, int(d[1])::2, :].cuda()
+        points, attributes, adjacency, offsets = scene.get_trace_data()
+        start = torch.full(ray_batch.shape[:-1], starts[v], dtype=torch.int64, device="cuda").to(torch.uint32)
+        rgba, _, contribution, _, _ = mod.TraceRays.apply(ref_pipe, points, attributes, adjacency, offsets, ray_batch,
+                                                          start, None, True)
+        rgb = rgba[..., :3] + (1 - rgba[..., -1:])
+        (rgb_batch - rgb).abs().mean(dim=-1).sum().backward()
+        want_err += scene.primal_points.grad.norm(dim=-1, keepdim=True).detach()
+        want_contrib = torch.maximum(want_contrib, contribution.detach())
+        for t in (scene.primal_points, scene.att_dc, scene.att_sh, scene.density):
+            t.grad = None
+    assert float((err - want_err).abs().max() / want_err.abs().max()) <= 1e-5
+    assert float((contrib - want_contrib).abs().max() / want_contrib.abs().max()) <= 1e-5
+    assert float((contrib > 0).float().mean()) > 0.02
