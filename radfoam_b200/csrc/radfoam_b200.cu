@@ -266,15 +266,24 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
                        reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
         RFB_LAUNCHED();
     } else if (n) {
-        int grid = grid_for((uint64_t)n * 32, 256);
-        if (p->attr_dtype == RFB_FLOAT16)
-            RFB_LAUNCH((build_cells_kernel<__half>), grid, 256, 0, stream, points,
-                       reinterpret_cast<const __half *>(attrs), n, A, SR,
-                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
-        else
-            RFB_LAUNCH((build_cells_kernel<float>), grid, 256, 0, stream, points,
-                       reinterpret_cast<const float *>(attrs), n, A, SR,
-                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+        const int grid = grid_for((uint64_t)n * (SR / 4), 256 * 4, 148 * 8);
+        float4 *cells = reinterpret_cast<float4 *>(p->cells.ptr), *rows = reinterpret_cast<float4 *>(p->sh_rows.ptr);
+#define RFB_BUILD_CELLS(DEG)                                                                                       \
+    do {                                                                                                           \
+        if (p->attr_dtype == RFB_FLOAT16)                                                                          \
+            RFB_LAUNCH((build_cells_kernel<__half, DEG>), grid, 256, 0, stream, points,                            \
+                       reinterpret_cast<const __half *>(attrs), n, cells, rows);                                   \
+        else                                                                                                       \
+            RFB_LAUNCH((build_cells_kernel<float, DEG>), grid, 256, 0, stream, points,                             \
+                       reinterpret_cast<const float *>(attrs), n, cells, rows);                                    \
+    } while (0)
+        switch (p->sh_degree) {
+        case 0: RFB_BUILD_CELLS(0); break;
+        case 1: RFB_BUILD_CELLS(1); break;
+        case 2: RFB_BUILD_CELLS(2); break;
+        default: RFB_BUILD_CELLS(3); break;
+        }
+#undef RFB_BUILD_CELLS
         RFB_LAUNCHED();
     }
     if (need_faces) {
@@ -1036,16 +1045,26 @@ int rfb_trace_backward_finalize(rfb_pipeline *p, uint32_t num_points, float *poi
     if (num_points != p->acc_points)
         return fail("rfb_trace_backward_finalize: no accumulated gradients for this point count");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
-    int grid = grid_for((uint64_t)num_points * 32, 256);
+    const int A = attr_dim(p->sh_degree);
+    const int grid = grid_for((uint64_t)num_points * A, 256 * 4, 148 * 8);
     int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
     const float *acc_ptr = p->acc_external ? p->acc_external : reinterpret_cast<const float *>(p->acc.ptr);
-    if (p->attr_dtype == RFB_FLOAT16)
-        RFB_LAUNCH((finalize_grads_kernel<__half>), grid, 256, 0, stream, acc_ptr, num_points, A, SR, points_grad,
-                   reinterpret_cast<__half *>(attribute_grad), scrub);
-    else
-        RFB_LAUNCH((finalize_grads_kernel<float>), grid, 256, 0, stream, acc_ptr, num_points, A, SR, points_grad,
-                   reinterpret_cast<float *>(attribute_grad), scrub);
+#define RFB_FINALIZE(DEG)                                                                                          \
+    do {                                                                                                           \
+        if (p->attr_dtype == RFB_FLOAT16)                                                                          \
+            RFB_LAUNCH((finalize_grads_kernel<__half, DEG>), grid, 256, 0, stream, acc_ptr, num_points,            \
+                       points_grad, reinterpret_cast<__half *>(attribute_grad), scrub);                            \
+        else                                                                                                       \
+            RFB_LAUNCH((finalize_grads_kernel<float, DEG>), grid, 256, 0, stream, acc_ptr, num_points,             \
+                       points_grad, reinterpret_cast<float *>(attribute_grad), scrub);                             \
+    } while (0)
+    switch (p->sh_degree) {
+    case 0: RFB_FINALIZE(0); break;
+    case 1: RFB_FINALIZE(1); break;
+    case 2: RFB_FINALIZE(2); break;
+    default: RFB_FINALIZE(3); break;
+    }
+#undef RFB_FINALIZE
     RFB_LAUNCHED();
     return 0;
 }
