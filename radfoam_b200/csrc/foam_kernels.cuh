@@ -51,37 +51,45 @@ __device__ __forceinline__ float softplus_beta10_backward(float grad_out, float 
 
 // The re-layout straight from the model's parameters -- RadFoamScene.get_trace_data (scene.py:202-217) fused in:
 //   attributes = cat(att_dc, att_sh, activation_scale * softplus(density, beta=10)).to(attr_dtype)
-// is never materialised; the cast is applied per value (AttrT = __half: round to fp16, then widen).
-template <typename AttrT>
-__global__ void build_cells_params_kernel(const float *__restrict__ points, const float *__restrict__ att_dc,
-                                          const float *__restrict__ att_sh, const float *__restrict__ density,
-                                          float activation_scale, uint32_t num_points, int attr_dim_, int sh_row_,
-                                          float4 *__restrict__ cells, float *__restrict__ sh_rows) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const int rest = attr_dim_ - 4; // columns of att_sh
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < num_points; i += warps) {
-        float *dst = sh_rows + (uint64_t)i * sh_row_;
-        for (int s = lane; s < sh_row_; s += 32) {
-            float v = 0.0f;
-            if (s < 3)
-                v = att_dc[3 * (uint64_t)i + s];
-            else if (s < attr_dim_ - 1)
-                v = att_sh[(uint64_t)i * rest + (s - 3)];
-            dst[s] = (float)(AttrT)v;
-        }
-        if (lane == 0) {
-            const float sigma = activation_scale * softplus_beta10(density[i]);
-            cells[i] = make_float4(points[3 * (uint64_t)i], points[3 * (uint64_t)i + 1], points[3 * (uint64_t)i + 2],
-                                   (float)(AttrT)sigma);
-        }
+// is never materialised; the cast is applied per value (AttrT = __half: round to fp16, then widen).  Same flat
+// streaming form as build_cells_kernel.
+template <typename AttrT, int DEG>
+__global__ void __launch_bounds__(256) build_cells_params_kernel(const float *__restrict__ points,
+                                                                 const float *__restrict__ att_dc,
+                                                                 const float *__restrict__ att_sh,
+                                                                 const float *__restrict__ density,
+                                                                 float activation_scale, uint32_t num_points,
+                                                                 float4 *__restrict__ cells,
+                                                                 float4 *__restrict__ sh_rows) {
+    constexpr uint32_t A = attr_dim(DEG), VPR = sh_row(DEG) / 4, REST = A - 4; // REST: columns of att_sh
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)num_points * VPR;
+    auto value = [&](uint64_t i, uint32_t s) -> float {
+        float v = 0.0f;
+        if (s < 3)
+            v = att_dc[3 * i + s];
+        else if (s < A - 1)
+            v = att_sh[i * REST + (s - 3)];
+        return (float)(AttrT)v;
+    };
+#pragma unroll 4
+    for (uint64_t v = gid; v < total; v += stride) {
+        const uint64_t i = v / VPR;
+        const uint32_t s0 = 4u * (uint32_t)(v % VPR);
+        sh_rows[v] = make_float4(value(i, s0), value(i, s0 + 1), value(i, s0 + 2), value(i, s0 + 3));
+    }
+    for (uint64_t i = gid; i < num_points; i += stride) {
+        const float sigma = activation_scale * softplus_beta10(density[i]);
+        cells[i] = make_float4(points[3 * i], points[3 * i + 1], points[3 * i + 2], (float)(AttrT)sigma);
     }
 }
 
 // faces[padded_begin(i) + f] = half4(RN(points[adj[e]] - points[i]), 0),
 // nbr[...] = adj[e]  (the reference's prefetch_adjacent_diff_kernel,
-// pipeline.cu:546-568, writes the same values in CSR order).  16 lanes per row.
-__global__ void build_faces_kernel(const float *__restrict__ points, uint32_t num_points,
+// pipeline.cu:546-568, writes the same values in CSR order).  16 lanes per row; the neighbour's position is
+// gathered from the float4 cell mirror built just before (one 128-bit load instead of three scalar ones: the
+// gathers are what this pass is bound by).
+__global__ void build_faces_kernel(const float4 *__restrict__ cells, uint32_t num_points,
                                    const uint32_t *__restrict__ adj,
                                    const uint32_t *__restrict__ off, uint2 *__restrict__ faces,
                                    uint32_t *__restrict__ nbr) {
@@ -91,18 +99,16 @@ __global__ void build_faces_kernel(const float *__restrict__ points, uint32_t nu
     for (uint32_t i = group; i < num_points; i += stride) {
         uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
         uint32_t dst = padded_begin(a, i);
-        float px = __ldg(points + 3 * (uint64_t)i), py = __ldg(points + 3 * (uint64_t)i + 1),
-              pz = __ldg(points + 3 * (uint64_t)i + 2);
+        const float4 pi = ldg4(cells + i);
         uint32_t nf = b - a, nf4 = (nf + 3u) & ~3u;
         for (uint32_t f = lane; f < nf4; f += 16) {
             uint2 rec = make_uint2(0u, 0u); // pad: zero face, dp == 0 never wins
             uint32_t j = 0;
             if (f < nf) {
                 j = __ldg(adj + a + f);
-                float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
-                      qz = __ldg(points + 3 * (uint64_t)j + 2);
-                __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
-                __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
+                const float4 q = ldg4(cells + j);
+                __half2 hxy = __floats2half2_rn(__fsub_rn(q.x, pi.x), __fsub_rn(q.y, pi.y));
+                __half2 hzw = __floats2half2_rn(__fsub_rn(q.z, pi.z), 0.0f);
                 rec.x = *reinterpret_cast<uint32_t *>(&hxy);
                 rec.y = *reinterpret_cast<uint32_t *>(&hzw);
             }
@@ -982,37 +988,39 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const float *__rest
 
 // accumulator -> gradients of the model's PARAMETERS (the backward of get_trace_data fused in): the attribute
 // gradient is rounded to the attribute dtype and scrubbed exactly like attr_grad above, then split into
-// att_dc / att_sh and chained through activation_scale * softplus(density, beta=10).
-template <typename AttrT>
-__global__ void finalize_params_kernel(const float *__restrict__ acc, const float *__restrict__ density,
-                                       float activation_scale, uint32_t num_points, int attr_dim_, int sh_row_,
-                                       float *__restrict__ points_grad, float *__restrict__ att_dc_grad,
-                                       float *__restrict__ att_sh_grad, float *__restrict__ density_grad, int scrub) {
-    const int gr = sh_row_ + 4;
-    const int rest = attr_dim_ - 4;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < num_points; i += warps) {
-        const float *row = acc + (uint64_t)i * gr;
-        for (int s = lane; s < attr_dim_; s += 32) {
-            float v = (s < attr_dim_ - 1) ? row[s] : row[sh_row_];
-            AttrT o = (AttrT)v;
-            if (scrub && !isfinite((float)o))
-                o = (AttrT)0.0f;
-            const float g = (float)o;
-            if (s < 3)
-                att_dc_grad[3 * (uint64_t)i + s] = g;
-            else if (s < attr_dim_ - 1)
-                att_sh_grad[(uint64_t)i * rest + (s - 3)] = g;
-            else
-                density_grad[i] = softplus_beta10_backward(g * activation_scale, density[i]);
-        }
-        if (lane < 3) {
-            float gq = row[sh_row_ + 1 + lane];
-            if (scrub && !isfinite(gq))
-                gq = 0.0f;
-            points_grad[3 * (uint64_t)i + lane] = gq;
-        }
+// att_dc / att_sh and chained through activation_scale * softplus(density, beta=10).  Flat streaming form.
+template <typename AttrT, int DEG>
+__global__ void __launch_bounds__(256) finalize_params_kernel(const float *__restrict__ acc,
+                                                              const float *__restrict__ density,
+                                                              float activation_scale, uint32_t num_points,
+                                                              float *__restrict__ points_grad,
+                                                              float *__restrict__ att_dc_grad,
+                                                              float *__restrict__ att_sh_grad,
+                                                              float *__restrict__ density_grad, int scrub) {
+    constexpr uint32_t A = attr_dim(DEG), SR = sh_row(DEG), GR = grad_row(DEG), REST = A - 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)num_points * A;
+#pragma unroll 4
+    for (uint64_t e = gid; e < total; e += stride) {
+        const uint64_t i = e / A;
+        const uint32_t s = (uint32_t)(e % A);
+        AttrT o = (AttrT)acc[i * GR + (s < A - 1 ? s : SR)];
+        if (scrub && !isfinite((float)o))
+            o = (AttrT)0.0f;
+        const float g = (float)o;
+        if (s < 3)
+            att_dc_grad[3 * i + s] = g;
+        else if (s < A - 1)
+            att_sh_grad[i * REST + (s - 3)] = g;
+        else
+            density_grad[i] = softplus_beta10_backward(g * activation_scale, density[i]);
+    }
+    const uint64_t total3 = (uint64_t)num_points * 3;
+    for (uint64_t e = gid; e < total3; e += stride) {
+        float g = acc[(e / 3) * GR + SR + 1 + (uint32_t)(e % 3)];
+        if (scrub && !isfinite(g))
+            g = 0.0f;
+        points_grad[e] = g;
     }
 }
 

@@ -255,15 +255,24 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     RFB_CUDA(p->cells.ensure((size_t)n * sizeof(float4)));
     RFB_CUDA(p->sh_rows.ensure((size_t)n * SR * sizeof(float)));
     if (n && p->params_bound) {
-        int grid = grid_for((uint64_t)n * 32, 256);
-        if (p->attr_dtype == RFB_FLOAT16)
-            RFB_LAUNCH((build_cells_params_kernel<__half>), grid, 256, 0, stream, points, p->params.att_dc,
-                       p->params.att_sh, p->params.density, p->params.activation_scale, n, A, SR,
-                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
-        else
-            RFB_LAUNCH((build_cells_params_kernel<float>), grid, 256, 0, stream, points, p->params.att_dc,
-                       p->params.att_sh, p->params.density, p->params.activation_scale, n, A, SR,
-                       reinterpret_cast<float4 *>(p->cells.ptr), reinterpret_cast<float *>(p->sh_rows.ptr));
+        const int grid = grid_for((uint64_t)n * (SR / 4), 256 * 4, 148 * 8);
+        float4 *cells = reinterpret_cast<float4 *>(p->cells.ptr), *rows = reinterpret_cast<float4 *>(p->sh_rows.ptr);
+#define RFB_BUILD_PARAMS(DEG)                                                                                      \
+    do {                                                                                                           \
+        if (p->attr_dtype == RFB_FLOAT16)                                                                          \
+            RFB_LAUNCH((build_cells_params_kernel<__half, DEG>), grid, 256, 0, stream, points, p->params.att_dc,   \
+                       p->params.att_sh, p->params.density, p->params.activation_scale, n, cells, rows);           \
+        else                                                                                                       \
+            RFB_LAUNCH((build_cells_params_kernel<float, DEG>), grid, 256, 0, stream, points, p->params.att_dc,    \
+                       p->params.att_sh, p->params.density, p->params.activation_scale, n, cells, rows);           \
+    } while (0)
+        switch (p->sh_degree) {
+        case 0: RFB_BUILD_PARAMS(0); break;
+        case 1: RFB_BUILD_PARAMS(1); break;
+        case 2: RFB_BUILD_PARAMS(2); break;
+        default: RFB_BUILD_PARAMS(3); break;
+        }
+#undef RFB_BUILD_PARAMS
         RFB_LAUNCHED();
     } else if (n) {
         const int grid = grid_for((uint64_t)n * (SR / 4), 256 * 4, 148 * 8);
@@ -296,8 +305,9 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
                        reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
             RFB_LAUNCHED();
         } else if (n) {
-            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream, points, n, adj,
-                       off, reinterpret_cast<uint2 *>(p->faces.ptr),
+            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream,
+                       reinterpret_cast<const float4 *>(p->cells.ptr), n, adj, off,
+                       reinterpret_cast<uint2 *>(p->faces.ptr),
                        reinterpret_cast<uint32_t *>(p->nbr.ptr));
             RFB_LAUNCHED();
         }
@@ -1098,18 +1108,28 @@ int rfb_trace_backward_finalize_params(rfb_pipeline *p, uint32_t num_points, flo
     if (num_points != p->acc_points)
         return fail("rfb_trace_backward_finalize_params: no accumulated gradients for this point count");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
-    int grid = grid_for((uint64_t)num_points * 32, 256);
+    const int A = attr_dim(p->sh_degree);
+    const int grid = grid_for((uint64_t)num_points * A, 256 * 4, 148 * 8);
     int scrub = (flags & RFB_FLAG_SCRUB_NONFINITE) ? 1 : 0;
     const float *acc_ptr = p->acc_external ? p->acc_external : reinterpret_cast<const float *>(p->acc.ptr);
-    if (p->attr_dtype == RFB_FLOAT16)
-        RFB_LAUNCH((finalize_params_kernel<__half>), grid, 256, 0, stream, acc_ptr, p->params.density,
-                   p->params.activation_scale, num_points, A, SR, points_grad, att_dc_grad, att_sh_grad,
-                   density_grad, scrub);
-    else
-        RFB_LAUNCH((finalize_params_kernel<float>), grid, 256, 0, stream, acc_ptr, p->params.density,
-                   p->params.activation_scale, num_points, A, SR, points_grad, att_dc_grad, att_sh_grad,
-                   density_grad, scrub);
+#define RFB_FINALIZE_PARAMS(DEG)                                                                                   \
+    do {                                                                                                           \
+        if (p->attr_dtype == RFB_FLOAT16)                                                                          \
+            RFB_LAUNCH((finalize_params_kernel<__half, DEG>), grid, 256, 0, stream, acc_ptr, p->params.density,    \
+                       p->params.activation_scale, num_points, points_grad, att_dc_grad, att_sh_grad,              \
+                       density_grad, scrub);                                                                       \
+        else                                                                                                       \
+            RFB_LAUNCH((finalize_params_kernel<float, DEG>), grid, 256, 0, stream, acc_ptr, p->params.density,     \
+                       p->params.activation_scale, num_points, points_grad, att_dc_grad, att_sh_grad,              \
+                       density_grad, scrub);                                                                       \
+    } while (0)
+    switch (p->sh_degree) {
+    case 0: RFB_FINALIZE_PARAMS(0); break;
+    case 1: RFB_FINALIZE_PARAMS(1); break;
+    case 2: RFB_FINALIZE_PARAMS(2); break;
+    default: RFB_FINALIZE_PARAMS(3); break;
+    }
+#undef RFB_FINALIZE_PARAMS
     RFB_LAUNCHED();
     return 0;
 }

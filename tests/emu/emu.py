@@ -173,6 +173,27 @@ class EmuPipeline:
             product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
         return out
 
+    def bind_scene_params(self, att_dc, att_sh, density, activation_scale=1.0):
+        """rfb_bind_scene_params (None unbinds); the arrays are kept alive here, like the product's Python layer does."""
+        if att_dc is None:
+            self._params = None
+            _check(self.lib.rfb_bind_scene_params(self.handle, None))
+            return
+        self._params = [_c(a, np.float32) for a in (att_dc, att_sh, density)]
+        sp = product_abi.SceneParams(self._params[0].ctypes.data, self._params[1].ctypes.data if self._params[1].size else None,
+                                     self._params[2].ctypes.data, float(activation_scale))
+        _check(self.lib.rfb_bind_scene_params(self.handle, ctypes.byref(sp)))
+
+    def trace_backward_finalize_params(self, num_points, scrub_nonfinite=False):
+        out = {"points_grad": np.empty((num_points, 3), np.float32), "att_dc_grad": np.empty((num_points, 3), np.float32),
+               "att_sh_grad": np.empty((num_points, self.attr_dim - 4), np.float32),
+               "density_grad": np.empty((num_points, 1), np.float32)}
+        _check(self.lib.rfb_trace_backward_finalize_params(
+            self.handle, num_points, _p(out["points_grad"]), _p(out["att_dc_grad"]),
+            _p(out["att_sh_grad"]) if out["att_sh_grad"].size else None, _p(out["density_grad"]),
+            product_abi.FLAG_SCRUB_NONFINITE if scrub_nonfinite else 0, None))
+        return out
+
     def reduce_finalize_peers(self, rank, accumulators, scrub_nonfinite=False, multicast=False):
         """rfb_reduce_finalize_peers with `accumulators` (one [N, grad_row] float32 array per rank) standing in for
         the peer-mapped buffers; returns THIS rank's writes into every rank's outputs as (attr_grads, points_grads),

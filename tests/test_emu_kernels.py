@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import common
+from radfoam_b200 import foam
 from oracle import oracle
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
@@ -294,6 +295,52 @@ print("ok")
     env = dict(os.environ, RFB_EMU_SHUFFLE=seed)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("deg,dtype", [(3, np.float32), (1, np.float32), (0, np.float32), (3, np.float16)])
+def test_parameter_form_scene(deg, dtype):
+    """SURVEY.md §8f.2 on the CPU: with a bound parameter-form scene the re-layout kernel evaluates
+    attributes = cat(att_dc, att_sh, scale * softplus(density, beta=10)).to(dtype) itself and the finalize kernel
+    returns the parameters' gradients (chain rule through cat and softplus) -- against the attribute-form path fed
+    with the same values."""
+    f = foam.small_foam(200, sh_degree=deg, seed=4)
+    rng = np.random.default_rng(8)
+    n, adim = f.num_points, f.attributes.shape[1]
+    att_dc, att_sh = f.attributes[:, :3].copy(), f.attributes[:, 3:adim - 1].copy()
+    raw = rng.normal(0.0, 0.4, size=(n, 1)).astype(np.float32)
+    raw[:3, 0] = [2.5, -3.0, 0.0]          # beyond softplus' linear threshold (x * beta > 20), deep in the tail, at 0
+    scale = np.float32(1.7)
+    xb = raw * np.float32(10.0)
+    sigma = scale * np.where(xb > 20.0, raw, np.log1p(np.exp(xb.astype(np.float64))).astype(np.float32) / np.float32(10.0))
+    attrs = np.concatenate([att_dc, att_sh, sigma.astype(np.float32)], axis=1).astype(dtype)
+    rays = foam.pinhole_rays(24, 16, (0, 0, -3), fov=0.7, up=(0, 1, 0))
+    start = np.full((16, 24), foam.nearest_point(f.points, (0, 0, -3)), dtype=np.uint32)
+    dq = np.tile(np.array([0.7, 0.3], dtype=np.float32), (16, 24, 1))
+    g = rng.normal(size=(16, 24, 4)).astype(dtype)
+    gd = (rng.normal(size=(16, 24, 2)) * 1e-3).astype(np.float32)
+    plain = emu.EmuPipeline(deg, dtype)
+    want = plain.trace_forward(f.points, attrs, f.adjacency, f.offsets, rays, start, dq)
+    wb = plain.trace_backward(f.points, attrs, f.adjacency, f.offsets, rays, start, want["rgba"], g, dq,
+                              want["depth_indices"], gd, scrub_nonfinite=True)
+    pipe = emu.EmuPipeline(deg, dtype)
+    pipe.bind_scene_params(att_dc, att_sh, raw, scale)
+    got = pipe.trace_forward(f.points, attrs, f.adjacency, f.offsets, rays, start, dq)   # `attrs` is ignored while bound
+    assert np.array_equal(got["num_intersections"], want["num_intersections"])
+    assert np.array_equal(got["depth_indices"], want["depth_indices"])
+    np.testing.assert_allclose(got["rgba"].astype(np.float32), want["rgba"].astype(np.float32), rtol=2e-6, atol=2e-6)
+    pipe.trace_backward_accumulate(f.points, attrs, f.adjacency, f.offsets, rays, start, got["rgba"], g, dq,
+                                   got["depth_indices"], gd)
+    gb = pipe.trace_backward_finalize_params(n, scrub_nonfinite=True)
+    tol = 2e-3 if dtype == np.float16 else 2e-5
+    ag = wb["attr_grad"].astype(np.float32)
+    assert common.grad_error(gb["points_grad"], wb["points_grad"]) <= 2e-5
+    assert common.grad_error(gb["att_dc_grad"], ag[:, :3]) <= tol
+    if adim > 4:
+        assert common.grad_error(gb["att_sh_grad"], ag[:, 3:adim - 1]) <= tol
+    z = np.exp(xb.astype(np.float64))
+    chain = np.where(xb > 20.0, 1.0, z / (z + 1.0)) * float(scale)
+    assert common.grad_error(gb["density_grad"], (ag[:, -1:].astype(np.float64) * chain).astype(np.float32)) <= tol
+    pipe.bind_scene_params(None, None, None)
 
 
 @pytest.mark.parametrize("multicast", [False, True], ids=["peer_pointers", "nvswitch_multicast"])
