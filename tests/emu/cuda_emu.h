@@ -443,11 +443,6 @@ inline void rfb_emu_red_add_v4(float *p, float a, float b, float c, float d) {
     atomicAdd(p + 3, d);
 }
 
-inline void rfb_emu_count_vote(bool needed) { // one call per lane; 32 lanes vote together
-    emu::counters.votes.fetch_add(1, std::memory_order_relaxed);
-    if (!needed)
-        emu::counters.votes_skipped.fetch_add(1, std::memory_order_relaxed);
-}
 inline void rfb_emu_red_add_v2(float *p, float a, float b) {
     emu::counters.red_v2.fetch_add(1, std::memory_order_relaxed);
     atomicAdd(p, a);

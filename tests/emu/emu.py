@@ -328,11 +328,3 @@ def red_counters(reset: bool = True) -> dict:
     load().rfe_counters(ctypes.byref(v4), ctypes.byref(v2), ctypes.byref(coll), 1 if reset else 0)
     return {"red_v4": v4.value, "red_v2": v2.value, "bytes": 16 * v4.value + 8 * v2.value,
             "warp_collectives": coll.value}
-
-
-def vote_counters(reset: bool = True) -> dict:
-    """Warp-level face-chunk votes of the experimental voted forward scan and how many of them skipped the chunk."""
-    votes, skipped = ctypes.c_uint64(), ctypes.c_uint64()
-    load().rfe_vote_counters(ctypes.byref(votes), ctypes.byref(skipped), 1 if reset else 0)
-    return {"chunk_votes": votes.value, "skipped": skipped.value,
-            "skipped_fraction": skipped.value / votes.value if votes.value else 0.0}

@@ -34,15 +34,6 @@ extern "C" int rfe_tape_buffers(rfb_pipeline *p, const void **pool, const void *
 }
 
 // Counters of the emulated reductions (16-byte, 8-byte) since the last reset.
-extern "C" void rfe_vote_counters(uint64_t *votes, uint64_t *skipped, int reset) {
-    *votes = emu::counters.votes.load() / 32; // counted per lane
-    *skipped = emu::counters.votes_skipped.load() / 32;
-    if (reset) {
-        emu::counters.votes = 0;
-        emu::counters.votes_skipped = 0;
-    }
-}
-
 extern "C" void rfe_counters(uint64_t *red_v4, uint64_t *red_v2, uint64_t *collectives, int reset) {
     *red_v4 = emu::counters.red_v4.load();
     *red_v2 = emu::counters.red_v2.load();
