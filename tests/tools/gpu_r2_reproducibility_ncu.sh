@@ -9,10 +9,6 @@ for i in 1 2 3 4 5; do
 done
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --emulate-shard 8 > gpurun_out/r2_bench_shard8.json 2> gpurun_out/r2_bench_shard8.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r2_bench_ref.json 2> gpurun_out/r2_bench_ref.err
-for v in default k64 k32; do
-  lib=tests/tools/_variants/libradfoam_b200_$v.so; [ $v = default ] && lib=default
-  timeout 300 python tests/tools/kblock_bench.py $lib $v > gpurun_out/r2_kblock_$v.log 2>&1
-done
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"forward_record_kernel|backward_cached_kernel" -s 6 -c 2 \
     -o gpurun_out/r2_prof_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"forward_record_kernel|backward_cached_kernel" -s 6 -c 2 \
@@ -28,4 +24,3 @@ try:
 except Exception as e: print($i, "ERR", e)
 P
 done
-cat gpurun_out/r2_kblock_*.log | grep '^{' | cut -c1-400
