@@ -115,3 +115,42 @@ def test_pipeline_methods_take_the_reference_binding_arguments():
     sig = inspect.signature(Pipeline.trace_forward).parameters
     assert sig["depth_quantiles"].default is None and sig["return_contribution"].default is False
     assert inspect.signature(create_pipeline).parameters["attr_dtype"].default == "float32"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ in the signatures) and a C program that
+    binds the path's entry points must link against the library and run without a GPU (argument checks only)."""
+    import subprocess
+
+    from radfoam_b200 import _lib
+
+    src = tmp_path / "bind.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "radfoam_b200.h"
+int main(void) {
+    rfb_pipeline *p = NULL;
+    rfb_trace_settings s = {0.001f, 1024};
+    rfb_launch_opts o = {0, 0, 0};
+    rfb_scene_params sp = {NULL, NULL, NULL, 1.0f};
+    rfb_multicast mc = {NULL, NULL, NULL};
+    (void)sp; (void)mc;
+    if (rfb_abi_version() != RFB_ABI_VERSION) return 1;
+    if (rfb_create_pipeline(3, RFB_FLOAT32, &p) != 0 || rfb_attribute_dim(p) != 49) return 2;
+    /* NULL scene arrays are rejected before anything touches the device */
+    if (rfb_trace_forward(p, &s, 1, NULL, NULL, 0, NULL, NULL, 1, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, NULL, &o, NULL) == 0) return 3;
+    if (!strstr(rfb_last_error(), "NULL")) return 4;
+    if (rfb_create_pipeline(9, RFB_FLOAT32, &p) == 0) return 5;
+    puts(rfb_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "bind"
+    lib_dir = os.path.dirname(_lib.library_path())
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src),
+                           "-o", str(exe), f"-L{lib_dir}", "-lradfoam_b200", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "Unsupported SH degree" in out.stdout
