@@ -86,10 +86,10 @@ __global__ void __launch_bounds__(256) build_cells_params_kernel(const float *__
 
 // faces[padded_begin(i) + f] = half4(RN(points[adj[e]] - points[i]), 0),
 // nbr[...] = adj[e]  (the reference's prefetch_adjacent_diff_kernel,
-// pipeline.cu:546-568, writes the same values in CSR order).  16 lanes per row; the neighbour's position is
-// gathered from the float4 cell mirror built just before (one 128-bit load instead of three scalar ones: the
-// gathers are what this pass is bound by).
-__global__ void build_faces_kernel(const float4 *__restrict__ cells, uint32_t num_points,
+// pipeline.cu:546-568, writes the same values in CSR order).  16 lanes per row.  Bound by the 16 M neighbour
+// gathers (L2): 101 us at 1 M points; gathering from the float4 cell mirror instead of the packed points (one
+// 128-bit load instead of three scalar ones) was measured and is slower (108.6 us: a third more bytes per gather).
+__global__ void build_faces_kernel(const float *__restrict__ points, uint32_t num_points,
                                    const uint32_t *__restrict__ adj,
                                    const uint32_t *__restrict__ off, uint2 *__restrict__ faces,
                                    uint32_t *__restrict__ nbr) {
@@ -99,16 +99,18 @@ __global__ void build_faces_kernel(const float4 *__restrict__ cells, uint32_t nu
     for (uint32_t i = group; i < num_points; i += stride) {
         uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
         uint32_t dst = padded_begin(a, i);
-        const float4 pi = ldg4(cells + i);
+        float px = __ldg(points + 3 * (uint64_t)i), py = __ldg(points + 3 * (uint64_t)i + 1),
+              pz = __ldg(points + 3 * (uint64_t)i + 2);
         uint32_t nf = b - a, nf4 = (nf + 3u) & ~3u;
         for (uint32_t f = lane; f < nf4; f += 16) {
             uint2 rec = make_uint2(0u, 0u); // pad: zero face, dp == 0 never wins
             uint32_t j = 0;
             if (f < nf) {
                 j = __ldg(adj + a + f);
-                const float4 q = ldg4(cells + j);
-                __half2 hxy = __floats2half2_rn(__fsub_rn(q.x, pi.x), __fsub_rn(q.y, pi.y));
-                __half2 hzw = __floats2half2_rn(__fsub_rn(q.z, pi.z), 0.0f);
+                float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
+                      qz = __ldg(points + 3 * (uint64_t)j + 2);
+                __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
+                __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
                 rec.x = *reinterpret_cast<uint32_t *>(&hxy);
                 rec.y = *reinterpret_cast<uint32_t *>(&hzw);
             }

@@ -305,9 +305,8 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
                        reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
             RFB_LAUNCHED();
         } else if (n) {
-            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream,
-                       reinterpret_cast<const float4 *>(p->cells.ptr), n, adj, off,
-                       reinterpret_cast<uint2 *>(p->faces.ptr),
+            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream, points, n, adj,
+                       off, reinterpret_cast<uint2 *>(p->faces.ptr),
                        reinterpret_cast<uint32_t *>(p->nbr.ptr));
             RFB_LAUNCHED();
         }
