@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(256) tile_steps_kernel(const uint2 *__restrict
             longest = max(longest, per_ray[r].x);
     }
     longest = __reduce_max_sync(0xffffffffu, longest);
+
     if (lane == 0)
         tile_steps[tile] = longest;
 }

@@ -57,6 +57,7 @@ struct Tls {
     dim3 bdim, gdim;
     Warp *warp = nullptr;
     unsigned lane = 0;
+    unsigned participants = 0; // lanes that took part in this fiber's last warp collective
 };
 
 struct Fiber {
@@ -128,6 +129,9 @@ inline std::array<uint64_t, 32> gather(unsigned mask, uint64_t v) {
     }
     std::array<uint64_t, 32> out;
     std::memcpy(out.data(), r.vals, sizeof(r.vals));
+    // the lanes whose values are valid: those that ARRIVED -- not "those that have not exited by now" (a fast lane
+    // may finish the kernel before a slow one gets to read the round)
+    self->t.participants = r.arrived;
     run->progress++;
     if (--r.readers == 0) {
         r.ready = false;
@@ -456,7 +460,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     auto v = emu::gather(mask, pred ? 1 : 0);
     unsigned out = 0;
     for (unsigned l = 0; l < 32; ++l)
-        if (((mask & ~emu::cur->t.warp->exited) >> l & 1u) && v[l])
+        if ((emu::cur->t.participants >> l & 1u) && v[l])
             out |= 1u << l;
     return out;
 }
@@ -465,7 +469,7 @@ inline unsigned __reduce_max_sync(unsigned mask, unsigned value) {
     auto v = emu::gather(mask, value);
     unsigned out = 0;
     for (unsigned l = 0; l < 32; ++l)
-        if ((mask & ~emu::cur->t.warp->exited) >> l & 1u)
+        if (emu::cur->t.participants >> l & 1u)
             out = std::max(out, (unsigned)v[l]);
     return out;
 }
@@ -473,7 +477,7 @@ inline unsigned __match_any_sync(unsigned mask, unsigned value) {
     auto v = emu::gather(mask, value);
     unsigned out = 0;
     for (unsigned l = 0; l < 32; ++l)
-        if (((mask & ~emu::cur->t.warp->exited) >> l & 1u) && (unsigned)v[l] == value)
+        if ((emu::cur->t.participants >> l & 1u) && (unsigned)v[l] == value)
             out |= 1u << l;
     return out;
 }

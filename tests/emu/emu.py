@@ -321,6 +321,16 @@ def tape_records(pipe: EmuPipeline, height: int, width: int):
     return cells, t1, count
 
 
+def tape_schedule(pipe: EmuPipeline):
+    """(tile_steps, order) of the last recording forward's replay schedule, or None when it was not scheduled."""
+    lib = load()
+    steps, order, blocks = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint32()
+    if lib.rfe_tape_schedule(pipe.handle, ctypes.byref(steps), ctypes.byref(order), ctypes.byref(blocks)):
+        return None
+    as_arr = lambda p: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), (blocks.value,)).copy()  # noqa: E731
+    return as_arr(steps), as_arr(order)
+
+
 def red_counters(reset: bool = True) -> dict:
     """16-byte / 8-byte global reductions and warp-collective operations (shuffles, votes, matches, syncs) the
     emulated kernels executed since the last reset."""

@@ -33,6 +33,16 @@ extern "C" int rfe_tape_buffers(rfb_pipeline *p, const void **pool, const void *
     return 0;
 }
 
+// Debug accessor: the replay schedule of the last recording forward (tile step counts and tile order).
+extern "C" int rfe_tape_schedule(rfb_pipeline *p, const uint32_t **tile_steps, const uint32_t **order, uint32_t *blocks) {
+    if (!p || !p->tape_valid || !p->tape_scheduled)
+        return 1;
+    *tile_steps = reinterpret_cast<const uint32_t *>(p->tape_sched.ptr);
+    *order = *tile_steps + p->tape_blocks;
+    *blocks = p->tape_blocks;
+    return 0;
+}
+
 // Counters of the emulated reductions (16-byte, 8-byte) since the last reset.
 extern "C" void rfe_counters(uint64_t *red_v4, uint64_t *red_v2, uint64_t *collectives, int reset) {
     *red_v4 = emu::counters.red_v4.load();

@@ -297,6 +297,26 @@ print("ok")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
 
+def test_replay_schedule_is_a_longest_first_permutation(long_walk_scene):
+    """The replay's tile order (small launches): tile_steps = the longest recorded walk of each 16x8 tile, order = a
+    permutation of the tiles with non-increasing tile_steps."""
+    case = long_walk_scene
+    pipe = emu.EmuPipeline(3)
+    for _ in range(2):
+        rec = pipe.trace_forward(*scene(case), case.rays, case.start, case.quantiles, scene_version=2, record_tape=True)
+    sched = emu.tape_schedule(pipe)
+    assert sched is not None
+    steps, order = sched
+    h, w = case.rays.shape[:2]
+    bx, by = (w + 15) // 16, (h + 7) // 8
+    assert steps.shape == (bx * by,) and sorted(order.tolist()) == list(range(bx * by))
+    assert np.all(np.diff(steps[order].astype(np.int64)) <= 0)
+    cells, t1, count = emu.tape_records(pipe, h, w)          # [warps][steps][32], 4 warps per tile
+    want = count.reshape(bx * by, 4 * 32).max(axis=1)
+    assert np.array_equal(steps, want.astype(np.uint32))
+    assert int(rec["num_intersections"].max()) >= int(steps.max())
+
+
 @pytest.mark.parametrize("deg,dtype", [(3, np.float32), (1, np.float32), (0, np.float32), (3, np.float16)])
 def test_parameter_form_scene(deg, dtype):
     """SURVEY.md §8f.2 on the CPU: with a bound parameter-form scene the re-layout kernel evaluates
