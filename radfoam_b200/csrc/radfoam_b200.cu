@@ -112,15 +112,6 @@ struct rfb_pipeline {
     // producer stream + completion event of the mirrors / of the tape: a consumer on another stream waits on it
     cudaStream_t scene_stream = nullptr, tape_stream = nullptr;
     cudaEvent_t scene_ready = nullptr, tape_ready = nullptr;
-    // A second, library-owned stream for work that is independent of what the caller's stream is doing: the face
-    // mirror is built there while the cell / SH mirror is built on the caller's stream (the two re-layout kernels
-    // read disjoint inputs and neither saturates the machine alone), and the gradient accumulator of a step is
-    // zero-filled there while the forward kernel runs.  Fork and join are events; never used while a CUDA graph
-    // is being captured (the step is then laid out serially on the captured stream).
-    cudaStream_t side = nullptr;
-    cudaEvent_t side_fork = nullptr, side_faces_done = nullptr, side_acc_zeroed = nullptr;
-    bool acc_prezeroed = false;      // the accumulator is being / has been zero-filled on `side` for the coming backward
-    uint32_t acc_prezeroed_points = 0;
     // RFB_DEBUG=1: checksum of (points, attributes) taken when the mirrors were built, re-checked on every cache hit
     DeviceBuffer debug_sum;
     uint64_t scene_checksum = 0;
@@ -229,27 +220,6 @@ int mark(cudaEvent_t &ev, cudaStream_t &producer, cudaStream_t stream) {
     return 0;
 }
 
-// Make the side stream wait for everything enqueued on `stream` so far (creates it on first use).
-int side_fork(rfb_pipeline *p, cudaStream_t stream) {
-    if (!p->side) {
-        RFB_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-        RFB_CUDA(cudaEventCreateWithFlags(&p->side_fork, cudaEventDisableTiming));
-        RFB_CUDA(cudaEventCreateWithFlags(&p->side_faces_done, cudaEventDisableTiming));
-        RFB_CUDA(cudaEventCreateWithFlags(&p->side_acc_zeroed, cudaEventDisableTiming));
-    }
-    RFB_CUDA(cudaEventRecord(p->side_fork, stream));
-    RFB_CUDA(cudaStreamWaitEvent(p->side, p->side_fork, 0));
-    return 0;
-}
-
-bool side_stream_enabled() {
-    static const bool on = [] {
-        const char *e = getenv("RFB_SIDE_STREAM"); // "0": everything on the caller's stream (for measuring)
-        return !(e && e[0] == '0');
-    }();
-    return on;
-}
-
 // (Re)build the internal mirrors of the scene unless the caller vouches they are current.
 int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *attrs, uint32_t e,
                  const uint32_t *adj, const uint32_t *off, bool need_faces,
@@ -284,33 +254,6 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
     const int A = attr_dim(p->sh_degree), SR = sh_row(p->sh_degree);
     RFB_CUDA(p->cells.ensure((size_t)n * sizeof(float4)));
     RFB_CUDA(p->sh_rows.ensure((size_t)n * SR * sizeof(float)));
-    // the face mirror first, on the side stream when there is one to use: it overlaps the cell / SH mirror below
-    bool faces_on_side = false;
-    if (need_faces) {
-        size_t slots = (size_t)padded_slots(n, e); // rows padded to 4 faces, <= 3 slack per row
-        RFB_CUDA(p->faces.ensure(slots * sizeof(uint2)));
-        RFB_CUDA(p->nbr.ensure(slots * sizeof(uint32_t)));
-        cudaStream_t fs = stream;
-        if (n && side_stream_enabled() && !capturing(stream)) {
-            if (int rc = side_fork(p, stream))
-                return rc;
-            fs = p->side;
-            faces_on_side = true;
-        }
-        if (n && caller_diff) {
-            RFB_LAUNCH((build_faces_from_diff_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, fs,
-                       reinterpret_cast<const uint2 *>(caller_diff), n, adj, off,
-                       reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
-            RFB_LAUNCHED();
-        } else if (n) {
-            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, fs, points, n, adj,
-                       off, reinterpret_cast<uint2 *>(p->faces.ptr),
-                       reinterpret_cast<uint32_t *>(p->nbr.ptr));
-            RFB_LAUNCHED();
-        }
-        if (faces_on_side)
-            RFB_CUDA(cudaEventRecord(p->side_faces_done, p->side));
-    }
     if (n && p->params_bound) {
         const int grid = grid_for((uint64_t)n * (SR / 4), 256 * 4, 148 * 8);
         float4 *cells = reinterpret_cast<float4 *>(p->cells.ptr), *rows = reinterpret_cast<float4 *>(p->sh_rows.ptr);
@@ -352,8 +295,22 @@ int ensure_scene(rfb_pipeline *p, uint32_t n, const float *points, const void *a
 #undef RFB_BUILD_CELLS
         RFB_LAUNCHED();
     }
-    if (faces_on_side)
-        RFB_CUDA(cudaStreamWaitEvent(stream, p->side_faces_done, 0)); // join before anything reads the faces
+    if (need_faces) {
+        size_t slots = (size_t)padded_slots(n, e); // rows padded to 4 faces, <= 3 slack per row
+        RFB_CUDA(p->faces.ensure(slots * sizeof(uint2)));
+        RFB_CUDA(p->nbr.ensure(slots * sizeof(uint32_t)));
+        if (n && caller_diff) {
+            RFB_LAUNCH((build_faces_from_diff_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream,
+                       reinterpret_cast<const uint2 *>(caller_diff), n, adj, off,
+                       reinterpret_cast<uint2 *>(p->faces.ptr), reinterpret_cast<uint32_t *>(p->nbr.ptr));
+            RFB_LAUNCHED();
+        } else if (n) {
+            RFB_LAUNCH((build_faces_kernel), grid_for((uint64_t)n * 16, 256), 256, 0, stream, points, n, adj,
+                       off, reinterpret_cast<uint2 *>(p->faces.ptr),
+                       reinterpret_cast<uint32_t *>(p->nbr.ptr));
+            RFB_LAUNCHED();
+        }
+    }
     k.faces = need_faces;
     p->key = k;
     p->key_valid = true;
@@ -639,13 +596,6 @@ void rfb_destroy_pipeline(rfb_pipeline *p) {
     for (auto &e : p->ev)
         if (e)
             cudaEventDestroy(e);
-    if (p->side) {
-        cudaStreamSynchronize(p->side);
-        cudaStreamDestroy(p->side);
-        cudaEventDestroy(p->side_fork);
-        cudaEventDestroy(p->side_faces_done);
-        cudaEventDestroy(p->side_acc_zeroed);
-    }
     if (p->scene_ready)
         cudaEventDestroy(p->scene_ready);
     if (p->tape_ready)
@@ -875,18 +825,6 @@ int rfb_trace_forward(rfb_pipeline *p, const rfb_trace_settings *settings, uint3
         return rc;
     if (int rc = profile_mark(p, 1, stream))
         return rc;
-    if (record && side_stream_enabled() && !capturing(stream) && num_points == p->acc_points && p->acc_points) {
-        // a backward over this forward is coming: zero-fill its gradient accumulator now, beside the forward kernel
-        float *acc_ptr = p->acc_external ? p->acc_external : reinterpret_cast<float *>(p->acc.ptr);
-        if (acc_ptr) {
-            if (int rc = side_fork(p, stream))
-                return rc;
-            RFB_CUDA(cudaMemsetAsync(acc_ptr, 0, (size_t)num_points * grad_row(p->sh_degree) * sizeof(float), p->side));
-            RFB_CUDA(cudaEventRecord(p->side_acc_zeroed, p->side));
-            p->acc_prezeroed = true;
-            p->acc_prezeroed_points = num_points;
-        }
-    }
     if (record) {
         // the replay's longest-first schedule (small launches only: see tape_order_kernel)
         const char *sched = getenv("RFB_REPLAY_ORDER"); // "0" never, "1" always (for measuring)
@@ -944,14 +882,7 @@ int rfb_trace_backward_accumulate(rfb_pipeline *p, const rfb_trace_settings *set
         RFB_CUDA(p->acc.ensure(acc_bytes));
         acc_ptr = reinterpret_cast<float *>(p->acc.ptr);
     }
-    if (p->acc_prezeroed && p->acc_prezeroed_points == num_points && !capturing(stream)) {
-        RFB_CUDA(cudaStreamWaitEvent(stream, p->side_acc_zeroed, 0)); // zero-filled beside the forward kernel
-    } else {
-        if (p->acc_prezeroed) // a fill for another size is in flight on the side stream: let it finish first
-            RFB_CUDA(cudaStreamWaitEvent(stream, p->side_acc_zeroed, 0));
-        RFB_CUDA(cudaMemsetAsync(acc_ptr, 0, acc_bytes, stream));
-    }
-    p->acc_prezeroed = false;
+    RFB_CUDA(cudaMemsetAsync(acc_ptr, 0, acc_bytes, stream));
     p->acc_points = num_points;
     if (num_rays == 0)
         return 0;
@@ -1032,9 +963,6 @@ int rfb_set_grad_accumulator(rfb_pipeline *p, float *ptr, uint64_t num_floats) {
         return fail("rfb_set_grad_accumulator: pipeline is NULL");
     if (ptr && (reinterpret_cast<uintptr_t>(ptr) & 15u))
         return fail("rfb_set_grad_accumulator: the accumulator must be 16-byte aligned");
-    if (p->acc_prezeroed && p->side) // a zero-fill of the previous accumulator may be in flight
-        cudaStreamSynchronize(p->side);
-    p->acc_prezeroed = false;
     p->acc_external = ptr;
     p->acc_external_floats = ptr ? num_floats : 0;
     p->acc_points = 0;

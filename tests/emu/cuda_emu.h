@@ -524,8 +524,6 @@ inline T __shfl_up_sync(unsigned mask, T value, unsigned delta, int width = 32) 
 #define cudaMemcpyAsync(d, s, n, kind, st) (std::memcpy((d), (s), (n)), cudaSuccess)
 #define cudaStreamSynchronize(s) (cudaSuccess)
 #define cudaStreamWaitEvent(s, e, f) (cudaSuccess)
-#define cudaStreamCreateWithFlags(s, f) (*(s) = nullptr, cudaSuccess)
-#define cudaStreamDestroy(s) (cudaSuccess)
 #define cudaStreamIsCapturing(s, st) (*(st) = cudaStreamCaptureStatusNone, cudaSuccess)
 #define cudaMemGetInfo(f, t) (*(f) = (size_t)1 << 40, *(t) = (size_t)1 << 40, cudaSuccess)
 #define cudaGetLastError() (cudaSuccess)
