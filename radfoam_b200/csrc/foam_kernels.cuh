@@ -93,29 +93,59 @@ __global__ void build_faces_kernel(const float *__restrict__ points, uint32_t nu
                                    const uint32_t *__restrict__ adj,
                                    const uint32_t *__restrict__ off, uint2 *__restrict__ faces,
                                    uint32_t *__restrict__ nbr) {
-    uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    uint32_t lane = threadIdx.x & 15;
-    uint32_t stride = (gridDim.x * blockDim.x) >> 4;
-    for (uint32_t i = group; i < num_points; i += stride) {
-        uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
-        uint32_t dst = padded_begin(a, i);
-        float px = __ldg(points + 3 * (uint64_t)i), py = __ldg(points + 3 * (uint64_t)i + 1),
-              pz = __ldg(points + 3 * (uint64_t)i + 2);
-        uint32_t nf = b - a, nf4 = (nf + 3u) & ~3u;
-        for (uint32_t f = lane; f < nf4; f += 16) {
-            uint2 rec = make_uint2(0u, 0u); // pad: zero face, dp == 0 never wins
-            uint32_t j = 0;
-            if (f < nf) {
-                j = __ldg(adj + a + f);
-                float qx = __ldg(points + 3 * (uint64_t)j), qy = __ldg(points + 3 * (uint64_t)j + 1),
-                      qz = __ldg(points + 3 * (uint64_t)j + 2);
-                __half2 hxy = __floats2half2_rn(__fsub_rn(qx, px), __fsub_rn(qy, py));
-                __half2 hzw = __floats2half2_rn(__fsub_rn(qz, pz), 0.0f);
-                rec.x = *reinterpret_cast<uint32_t *>(&hxy);
-                rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+    const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const uint32_t lane = threadIdx.x & 15;
+    const uint32_t stride = (gridDim.x * blockDim.x) >> 4;
+    // The pass is a chain of dependent loads per row (offsets -> adjacency -> neighbour point), so it is bound by
+    // how many rows are in flight: every 16-lane group works on kRows rows at once, level by level.
+    constexpr int kRows = 2;
+    for (uint32_t base = group; base < num_points; base += kRows * stride) {
+        uint32_t row[kRows], a[kRows], nf[kRows];
+        float px[kRows], py[kRows], pz[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) { // level 1: offsets and own point
+            row[k] = base + k * stride;
+            const bool live = row[k] < num_points;
+            const uint32_t i = live ? row[k] : base;
+            a[k] = __ldg(off + i);
+            nf[k] = live ? __ldg(off + i + 1) - a[k] : 0u;
+            px[k] = __ldg(points + 3 * (uint64_t)i);
+            py[k] = __ldg(points + 3 * (uint64_t)i + 1);
+            pz[k] = __ldg(points + 3 * (uint64_t)i + 2);
+        }
+        uint32_t passes = 0;
+#pragma unroll
+        for (int k = 0; k < kRows; ++k)
+            passes = max(passes, (nf[k] + 15u) >> 4);
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            const uint32_t f = 16u * pass + lane;
+            uint32_t j[kRows];
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) // level 2: neighbour ids
+                j[k] = f < nf[k] ? __ldg(adj + a[k] + f) : 0u;
+            float qx[kRows], qy[kRows], qz[kRows];
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) { // level 3: neighbour points
+                qx[k] = __ldg(points + 3 * (uint64_t)j[k]);
+                qy[k] = __ldg(points + 3 * (uint64_t)j[k] + 1);
+                qz[k] = __ldg(points + 3 * (uint64_t)j[k] + 2);
             }
-            faces[dst + f] = rec;
-            nbr[dst + f] = j;
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) {
+                const uint32_t nf4 = (nf[k] + 3u) & ~3u;
+                if (f < nf4) {
+                    uint2 rec = make_uint2(0u, 0u); // pad: zero face, dp == 0 never wins
+                    if (f < nf[k]) {
+                        __half2 hxy = __floats2half2_rn(__fsub_rn(qx[k], px[k]), __fsub_rn(qy[k], py[k]));
+                        __half2 hzw = __floats2half2_rn(__fsub_rn(qz[k], pz[k]), 0.0f);
+                        rec.x = *reinterpret_cast<uint32_t *>(&hxy);
+                        rec.y = *reinterpret_cast<uint32_t *>(&hzw);
+                    }
+                    const uint32_t dst = padded_begin(a[k], row[k]) + f;
+                    faces[dst] = rec;
+                    nbr[dst] = f < nf[k] ? j[k] : 0u;
+                }
+            }
         }
     }
 }
