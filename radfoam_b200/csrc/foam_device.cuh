@@ -100,35 +100,54 @@ __device__ __forceinline__ void multimem_st_v2(void *p, float2 v) {
 }
 
 // ---------------------------------------------------------------- SH basis
-// Real SH basis of the (unit) direction; same formulas and evaluation order as
-// sh_coefficients<deg>() (sh_utils.cuh:34-70) so nvcc contracts them alike.
+// Real SH basis of the (unit) direction (sh_coefficients<deg>(), sh_utils.cuh:34-70), with the multiply-add
+// association PINNED to what nvcc makes of the reference's source in its kernels (read from oracle/_ref's SASS):
+//   degree 2 (every square used at most twice, so the products are fused into the sums):
+//     2zz - xx - yy = fma(-y, y, fma(-x, x, fma(z, z, z*z)));   xx - yy = fma(x, x, -(y*y))
+//   degree 3 (the squares are shared by seven terms, so they are rounded products):
+//     2zz - xx - yy = ((zz + zz) - xx) - yy;   xx - yy a plain difference;   3xx - yy = fma(xx, 3, -yy);
+//     xx - 3yy = fma(yy, -3, xx);   4zz - xx - yy = fma(zz, 4, -xx) - yy;
+//     2zz - 3xx - 3yy = fma(yy, -3, fma(xx, -3, zz + zz));   c*u*(...) = (c*u)*(...);   c*xy*z = (c*xy)*z
+// Left to the compiler, the fusion depends on the surrounding kernel: round 2's warp-aggregated backward rounded
+// y*y where the forward had fused it, the two bases differed in the last bit, and with it the backward's recomputed
+// colour sum -- invisible at the default weight threshold, but with threshold 0 the late cells' gradients are
+// (saved colour - recomputed colour) / T and became rounding residue (1e-6 where the reference has 1e-14;
+// found by tests/test_gpu_fuzz.py).
 template <int DEG>
 __device__ __forceinline__ void sh_basis(float x, float y, float z, float *sh) {
     constexpr float C0 = 0.28209479177387814f;
     constexpr float C1 = 0.4886025119029199f;
     sh[0] = C0;
     if (DEG > 0) {
-        sh[1] = -C1 * y;
-        sh[2] = C1 * z;
-        sh[3] = -C1 * x;
+        sh[1] = __fmul_rn(-C1, y);
+        sh[2] = __fmul_rn(C1, z);
+        sh[3] = __fmul_rn(-C1, x);
     }
-    float xx = x * x, yy = y * y, zz = z * z;
-    float xy = x * y, yz = y * z, xz = x * z;
-    if (DEG > 1) {
-        sh[4] = 1.0925484305920792f * xy;
-        sh[5] = -1.0925484305920792f * yz;
-        sh[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-        sh[7] = -1.0925484305920792f * xz;
-        sh[8] = 0.5462742152960396f * (xx - yy);
+    if (DEG == 2) {
+        sh[4] = __fmul_rn(1.0925484305920792f, __fmul_rn(x, y));
+        sh[5] = __fmul_rn(-1.0925484305920792f, __fmul_rn(y, z));
+        sh[6] = __fmul_rn(0.31539156525252005f, __fmaf_rn(-y, y, __fmaf_rn(-x, x, __fmaf_rn(z, z, __fmul_rn(z, z)))));
+        sh[7] = __fmul_rn(-1.0925484305920792f, __fmul_rn(x, z));
+        sh[8] = __fmul_rn(0.5462742152960396f, __fmaf_rn(x, x, -__fmul_rn(y, y)));
     }
     if (DEG > 2) {
-        sh[9] = -0.5900435899266435f * y * (3.0f * xx - yy);
-        sh[10] = 2.890611442640554f * xy * z;
-        sh[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
-        sh[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-        sh[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
-        sh[14] = 1.445305721320277f * z * (xx - yy);
-        sh[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
+        const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+        const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+        const float zz2 = __fadd_rn(zz, zz);
+        const float xx_yy = __fsub_rn(xx, yy);
+        const float zz4_xx_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);
+        sh[4] = __fmul_rn(1.0925484305920792f, xy);
+        sh[5] = __fmul_rn(-1.0925484305920792f, yz);
+        sh[6] = __fmul_rn(0.31539156525252005f, __fsub_rn(__fsub_rn(zz2, xx), yy));
+        sh[7] = __fmul_rn(-1.0925484305920792f, xz);
+        sh[8] = __fmul_rn(0.5462742152960396f, xx_yy);
+        sh[9] = __fmul_rn(__fmul_rn(-0.5900435899266435f, y), __fmaf_rn(xx, 3.0f, -yy));
+        sh[10] = __fmul_rn(__fmul_rn(2.890611442640554f, xy), z);
+        sh[11] = __fmul_rn(__fmul_rn(-0.4570457994644658f, y), zz4_xx_yy);
+        sh[12] = __fmul_rn(__fmul_rn(0.3731763325901154f, z), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+        sh[13] = __fmul_rn(__fmul_rn(-0.4570457994644658f, x), zz4_xx_yy);
+        sh[14] = __fmul_rn(__fmul_rn(1.445305721320277f, z), xx_yy);
+        sh[15] = __fmul_rn(__fmul_rn(-0.5900435899266435f, x), __fmaf_rn(yy, -3.0f, xx));
     }
 }
 
